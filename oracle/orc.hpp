@@ -326,5 +326,7 @@ void CalcScalCls(Model& M);
 void InterpolateCls(Model& M);
 double ScalarPower(const Model& M, double k);
 int run_all(Model& M);                    // CAMB_GetResults for the scalar flat path
+int run_model(Model& M, double* stage_times, bool reuse_bessels);
+int load_highL_template(Model& M, const char* path);
 
 }  // namespace orc
