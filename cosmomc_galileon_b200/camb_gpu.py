@@ -1,0 +1,272 @@
+"""ctypes binding of libgalcamb_b200.so + a thin host class following CAMB's own stage order.
+
+Reference call sequence being mirrored (camb/cmbmain.f90:131-291):
+    InitVars -> SetkValuesForSources -> [loop DoSourcek] -> InitSourceInterpolation -> InitSpherBessels ->
+    SetkValuesForInt -> [loop SourceToTransfers] -> ClTransferToCl (CalcScalCls, InterpolateCls)
+The bracketed loops and the two routines after them are the GPU stages; everything before is the caller's
+(the Fortran host in production, a table fixture or the test oracle here) and arrives as ModelTables.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+MAX_NU, MAX_NQ, MAX_REGIONS = 3, 5, 16
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path():
+    return os.path.join(_HERE, "libgalcamb_b200.so")
+
+
+class Region(C.Structure):
+    _fields_ = [("Low", C.c_double), ("High", C.c_double), ("delta", C.c_double), ("start_index", C.c_int),
+                ("IsLog", C.c_int)]
+
+
+_D, _I, _P = C.c_double, C.c_int, C.POINTER(C.c_double)
+
+
+class CModel(C.Structure):
+    """struct galcamb_model of include/galcamb.h (field order must match)."""
+    _fields_ = (
+        [(n, _D) for n in ("grhom grhog grhor grhob grhoc grhov grhornomass grhok adotrad tau0 taurst taurend tau_maxvis "
+                           "tight_tau matter_verydom_tau epsw max_etak_scalar AccuracyBoost lAccuracyBoost").split()]
+        + [(n, _I) for n in ("use_galileon DoLateRadTruncation HighAccuracyDefault AccuratePolarization "
+                             "AccurateReionization WantLateTime MassiveNuMethod Nu_mass_eigenstates Num_Nu_massive "
+                             "nqmax").split()]
+        + [("grhormass", _D * MAX_NU), ("nu_masses", _D * MAX_NU), ("nu_q", _D * MAX_NQ), ("nu_int_kernel", _D * MAX_NQ),
+           ("nu_tau_notmassless", (_D * MAX_NU) * MAX_NQ), ("nu_tau_nonrelativistic", _D * MAX_NU),
+           ("nu_tau_massive", _D * MAX_NU), ("dlnam", _D)]
+        + [(n, _P) for n in "nu_r1 nu_p1 nu_dr1 nu_dp1 nu_ddr1 nu_ddp1".split()]
+        + [("nthermo", _I), ("tauminn", _D), ("dlntau", _D)]
+        + [(n, _P) for n in "cs2 dcs2 dotmu ddotmu dddotmu".split()]
+        + [("nt", _I)]
+        + [(n, _P) for n in "tau dtau vis dvis ddvis expmmu opac dopac".split()]
+        + [("n_tau_regions", _I), ("tau_regions", Region * MAX_REGIONS)]
+        + [(n, _D) for n in "c2 c3 c4 c5 cG h0 orad".split()]
+        + [("ngal", _I)]
+        + [(n, _P) for n in "gal_a gal_h gal_x".split()]
+        + [("nk", _I), ("k", _P), ("nq", _I), ("q", _P), ("dq", _P)]
+        + [(n, _D) for n in "ScalarPowerAmp an n_run n_runrun k_0_scalar".split()]
+        + [("lmax", _I)]
+    )
+
+
+SCALARS = [n for n, t in CModel._fields_ if t in (_D, _I)]
+ARRAYS = [n for n, t in CModel._fields_ if t is _P]
+SMALL = ["grhormass", "nu_masses", "nu_q", "nu_int_kernel", "nu_tau_notmassless", "nu_tau_nonrelativistic", "nu_tau_massive"]
+
+
+class ModelTables:
+    """The per-model state the host owns after InitVars, as numpy arrays + scalars (see galcamb_model)."""
+
+    def __init__(self, d):
+        self.d = {}
+        for k, v in d.items():
+            if k in ARRAYS:
+                self.d[k] = np.ascontiguousarray(v, dtype=np.float64)
+            elif k in ("ls", "tau_regions"):
+                self.d[k] = np.asarray(v)
+            elif k in SMALL:
+                self.d[k] = np.asarray(v, dtype=np.float64)
+            else:
+                self.d[k] = v
+        self._c = None
+
+    @classmethod
+    def load(cls, path):
+        z = np.load(path, allow_pickle=False)
+        return cls({k: (z[k] if z[k].ndim else z[k].item()) for k in z.files})
+
+    def save(self, path):
+        np.savez_compressed(path, **self.d)
+
+    def copy(self, **override):
+        d = dict(self.d)
+        d.update(override)
+        return ModelTables(d)
+
+    @property
+    def ls(self):
+        return np.asarray(self.d["ls"], dtype=np.int32)
+
+    def nbytes(self):
+        return sum(self.d[k].nbytes for k in ARRAYS if k in self.d)
+
+    def cstruct(self):
+        if self._c is not None:
+            return self._c
+        m = CModel()
+        d = self.d
+        for n in SCALARS:
+            if n != "n_tau_regions":
+                setattr(m, n, d[n])
+        for n in ARRAYS:
+            a = d.get(n)
+            setattr(m, n, a.ctypes.data_as(_P) if a is not None and a.size else None)
+        for n in ("grhormass", "nu_masses", "nu_tau_nonrelativistic", "nu_tau_massive"):
+            v = np.zeros(MAX_NU)
+            a = np.atleast_1d(d.get(n, []))
+            v[: len(a)] = a[:MAX_NU]
+            setattr(m, n, (_D * MAX_NU)(*v))
+        for n in ("nu_q", "nu_int_kernel"):
+            v = np.zeros(MAX_NQ)
+            a = np.atleast_1d(d.get(n, []))
+            v[: len(a)] = a[:MAX_NQ]
+            setattr(m, n, (_D * MAX_NQ)(*v))
+        t = np.zeros((MAX_NQ, MAX_NU))
+        a = np.atleast_2d(d.get("nu_tau_notmassless", np.zeros((0, 0))))
+        if a.size:
+            t[: a.shape[0], : a.shape[1]] = a
+        for i in range(MAX_NQ):
+            for j in range(MAX_NU):
+                m.nu_tau_notmassless[i][j] = t[i, j]
+        reg = np.asarray(d["tau_regions"], dtype=np.float64).reshape(-1, 5)
+        m.n_tau_regions = len(reg)
+        for i, r in enumerate(reg):
+            m.tau_regions[i] = Region(r[0], r[1], r[2], int(r[3]), int(r[4]))
+        self._c = m
+        return m
+
+
+_lib = None
+
+
+def load_library():
+    """Loads the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise RuntimeError("libgalcamb_b200.so is not built (run `python cosmomc_galileon_b200/build.py`); "
+                               "there is no CPU fallback")
+        L = C.CDLL(p)
+        L.galcamb_init_.argtypes = [C.POINTER(_I)]
+        L.galcamb_last_error_.restype = C.c_char_p
+        L.galcamb_set_bessels_.argtypes = [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_D)]
+        L.galcamb_get_bessels_.argtypes = [C.POINTER(_I), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.galcamb_set_template_.argtypes = [C.c_void_p, C.POINTER(_I)]
+        L.galcamb_batch_begin_.argtypes = [C.POINTER(_I)]
+        L.galcamb_set_model_.argtypes = [C.POINTER(_I), C.POINTER(CModel)]
+        L.galcamb_get_sources_.argtypes = [C.POINTER(_I), C.c_void_p]
+        L.galcamb_put_sources_.argtypes = [C.POINTER(_I), C.c_void_p]
+        L.galcamb_get_transfers_.argtypes = [C.POINTER(_I), C.c_void_p]
+        L.galcamb_get_cls_.argtypes = [C.POINTER(_I), C.c_void_p, C.c_void_p]
+        L.galcamb_get_status_.argtypes = [C.POINTER(_I), C.POINTER(_I)]
+        L.galcamb_batch_cls_.argtypes = [C.POINTER(CModel), C.POINTER(_I), C.c_void_p]
+        L.galcamb_get_timings_.argtypes = [C.c_void_p]
+        L.galcamb_get_counters_.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class GalCambError(RuntimeError):
+    pass
+
+
+class GalCamb:
+    """One GPU context.  Stage methods keep the reference's names."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        self._chk(self.L.galcamb_init_(C.byref(_I(device))))
+        self.models = []
+        self.nl = 0
+
+    def _chk(self, rc):
+        if rc:
+            raise GalCambError("galcamb error %d: %s" % (rc, self.L.galcamb_last_error_().decode()))
+
+    def close(self):
+        self.L.galcamb_free_()
+
+    # InitSpherBessels, camb/bessels.f90:34
+    def InitSpherBessels(self, ls, kmaxfile, AccuracyBoost=1.0):
+        ls = np.ascontiguousarray(ls, dtype=np.int32)
+        self.nl = len(ls)
+        self._chk(self.L.galcamb_set_bessels_(ls.ctypes.data_as(C.POINTER(_I)), C.byref(_I(len(ls))), C.byref(_I(int(kmaxfile))),
+                                              C.byref(_D(AccuracyBoost))))
+
+    def bessel_tables(self):
+        nx = _I(0)
+        self._chk(self.L.galcamb_get_bessels_(C.byref(nx), None, None, None))
+        xs = np.zeros(nx.value)
+        ajl = np.zeros((self.nl, nx.value))
+        ajlpr = np.zeros((self.nl, nx.value))
+        self._chk(self.L.galcamb_get_bessels_(C.byref(nx), xs.ctypes.data, ajl.ctypes.data, ajlpr.ctypes.data))
+        return xs, ajl, ajlpr
+
+    # CheckLoadedHighLTemplate, camb/modules.f90:1222 ; tmpl[type][l-2], type = TT,EE,TE
+    def set_template(self, tmpl):
+        if tmpl is None:
+            self._chk(self.L.galcamb_set_template_(None, C.byref(_I(0))))
+            return
+        t = np.ascontiguousarray(tmpl, dtype=np.float64)
+        assert t.shape[0] == 3
+        self._chk(self.L.galcamb_set_template_(t.ctypes.data, C.byref(_I(t.shape[1] + 1))))
+
+    def set_models(self, models):
+        self.models = list(models)
+        self._chk(self.L.galcamb_batch_begin_(C.byref(_I(len(self.models)))))
+        for i, m in enumerate(self.models):
+            self._chk(self.L.galcamb_set_model_(C.byref(_I(i)), C.byref(m.cstruct())))
+
+    # hot loop 1, camb/cmbmain.f90:201-206
+    def CalcScalarSources(self):
+        self._chk(self.L.galcamb_evolve_sources_())
+
+    # InitSourceInterpolation + hot loop 2, camb/cmbmain.f90:244, :263-267
+    def SourceToTransfers(self):
+        self._chk(self.L.galcamb_los_integrate_())
+
+    # ClTransferToCl, camb/cmbmain.f90:293
+    def ClTransferToCl(self):
+        self._chk(self.L.galcamb_scalar_cls_())
+
+    def Src(self, slot=0):
+        d = self.models[slot].d
+        S = 3 if d["WantLateTime"] else 2
+        out = np.zeros((d["nt"], S, d["nk"]))
+        self._chk(self.L.galcamb_get_sources_(C.byref(_I(slot)), out.ctypes.data))
+        return out
+
+    def put_Src(self, Src, slot=0):
+        a = np.ascontiguousarray(Src, dtype=np.float64)
+        self._chk(self.L.galcamb_put_sources_(C.byref(_I(slot)), a.ctypes.data))
+
+    def Delta_p_l_k(self, slot=0):
+        d = self.models[slot].d
+        S = 3 if d["WantLateTime"] else 2
+        out = np.zeros((d["nq"], self.nl, S))
+        self._chk(self.L.galcamb_get_transfers_(C.byref(_I(slot)), out.ctypes.data))
+        return out
+
+    def Cls(self, slot=0):
+        d = self.models[slot].d
+        nt = 6 if d["WantLateTime"] else 3
+        icl = np.zeros((nt, self.nl))
+        cl = np.zeros((nt, d["lmax"] - 1))
+        self._chk(self.L.galcamb_get_cls_(C.byref(_I(slot)), icl.ctypes.data, cl.ctypes.data))
+        return icl, cl
+
+    # one call for a batch: the public API timed end to end by bench.py
+    def batch_cls(self, models, out=None):
+        n = len(models)
+        arr = (CModel * n)(*[m.cstruct() for m in models])
+        self.models = list(models)
+        lmax = models[0].d["lmax"]
+        if out is None:
+            out = np.zeros((n, 3, lmax - 1))
+        self._chk(self.L.galcamb_batch_cls_(arr, C.byref(_I(n)), out.ctypes.data))
+        return out
+
+    def timings(self):
+        ms = np.zeros(8)
+        self.L.galcamb_get_timings_(ms.ctypes.data)
+        return dict(zip("evolve spline_k los cls h2d d2h bessel total".split(), ms))
+
+    def counters(self):
+        c = np.zeros(4)
+        self.L.galcamb_get_counters_(c.ctypes.data)
+        return dict(zip("n_derivs sum_n n_out n_iter".split(), c))

@@ -1,0 +1,606 @@
+// C ABI of libgalcamb_b200.so (see include/galcamb.h): context, model upload, stage launches, results.
+// Host-side helpers here are product code: table packing into the AoS device layout (model.h), the natural
+// cubic spline of the Galileon background (what gsl_spline_init does inside arrays_, camb/galileon.cc:666-682),
+// the running minimum used by Thermo_OpacityToTime, the BessRanges grid of camb/bessels.f90:68-76 and the
+// work-item ordering of the per-k kernel.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/galcamb.h"
+#include "model.h"
+
+extern "C" void gc_upload_constants();
+extern "C" cudaError_t gc_launch_evolve(const DevModel*, const int2*, int, double*, int, int*, unsigned long long*, cudaStream_t);
+extern "C" cudaError_t gc_set_bess_regions(const GcRegions*);
+extern "C" cudaError_t gc_launch_bessels(double2*, const double*, const int*, double*, int, int, cudaStream_t);
+extern "C" cudaError_t gc_launch_spline_k(const DevModel*, int, int, cudaStream_t);
+extern "C" cudaError_t gc_launch_los(const DevModel*, int, int, int, int, const double2*, const double*, const int*, int, int,
+                                     unsigned long long*, cudaStream_t);
+extern "C" cudaError_t gc_launch_zero(double*, size_t, cudaStream_t);
+extern "C" cudaError_t gc_launch_cls(const DevModel*, int, const int*, int, int, int, const double*, int, cudaStream_t);
+
+namespace {
+
+struct Slot {
+  bool set = false;
+  DevModel host{};          // device pointers filled in
+  double* d_tables = nullptr;  // one allocation: th | pmin | ts | gal | k | q | dq
+  size_t tables_cap = 0;
+  double* d_out = nullptr;     // Src | ddSrc | Delta | iCl | Cl
+  size_t out_cap = 0;
+  int lmax = 0, ntype = 3, status = 0;
+  std::vector<double> staging;
+};
+
+struct Ctx {
+  bool ready = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[10]{};
+  // Bessel tables
+  int nl = 0, nx = 0, kmaxfile = 0;
+  double bess_boost = 0;
+  std::vector<int> ls;
+  std::vector<double> xs;
+  int* d_ls = nullptr;
+  double* d_xs = nullptr;
+  double2* d_bess = nullptr;
+  // template
+  double* d_tmpl = nullptr;
+  int lmax_tmpl = 0;
+  // neutrino tables (cosmology independent; uploaded from the first model that has them)
+  double* d_nu_tab = nullptr;
+  bool nu_tab_set = false;
+  // batch
+  std::vector<Slot> slots;
+  DevModel* d_models = nullptr;
+  size_t models_cap = 0;
+  int2* d_items = nullptr;
+  size_t items_cap = 0;
+  int* d_status = nullptr;
+  double* d_ws = nullptr;
+  size_t ws_cap = 0;
+  unsigned long long* d_counters = nullptr;  // [0..2] evolve, [3] n_iter
+  std::vector<int2> items;
+  double ms[8] = {0};
+  double counters[4] = {0};
+  std::string err;
+};
+
+Ctx g;
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      g.err = std::string(#call) + ": " + cudaGetErrorString(e_);                                  \
+      return 100;                                                                                  \
+    }                                                                                              \
+  } while (0)
+
+int fail(int code, const char* msg) {
+  g.err = msg;
+  return code;
+}
+
+// natural cubic spline, c[i] = y''(x_i)/2 (the representation gsl_interp_cspline keeps)
+void natural_spline_c(const std::vector<double>& xa, const std::vector<double>& ya, std::vector<double>& c) {
+  const int n = (int)xa.size();
+  const int sys = n - 2;
+  c.assign(n, 0.0);
+  std::vector<double> g_(sys), diag(sys), off(sys), al(sys), ga(sys), z(sys);
+  for (int i = 0; i < sys; i++) {
+    const double h_i = xa[i + 1] - xa[i], h_ip1 = xa[i + 2] - xa[i + 1];
+    const double yd_i = ya[i + 1] - ya[i], yd_ip1 = ya[i + 2] - ya[i + 1];
+    const double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0, g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
+    off[i] = h_ip1;
+    diag[i] = 2.0 * (h_ip1 + h_i);
+    g_[i] = 3.0 * (yd_ip1 * g_ip1 - yd_i * g_i);
+  }
+  al[0] = diag[0];
+  ga[0] = off[0] / al[0];
+  for (int i = 1; i < sys - 1; i++) {
+    al[i] = diag[i] - off[i - 1] * ga[i - 1];
+    ga[i] = off[i] / al[i];
+  }
+  if (sys > 1) al[sys - 1] = diag[sys - 1] - off[sys - 2] * ga[sys - 2];
+  z[0] = g_[0];
+  for (int i = 1; i < sys; i++) z[i] = g_[i] - ga[i - 1] * z[i - 1];
+  for (int i = 0; i < sys; i++) z[i] = z[i] / al[i];
+  c[sys] = z[sys - 1];
+  for (int i = sys - 2; i >= 0; i--) c[i + 1] = z[i] - ga[i] * c[i + 2];
+}
+
+// BessRanges of camb/bessels.f90:68-76: five adjacent, non-overlapping regions, so the general merge rules of
+// Ranges_Add (camb/utils.F90:206-466) reduce to "n = max(1,int(span/delta + 1 - 0.1)), step = span/n" per region.
+void build_bess_ranges(int kmaxfile, double boost, GcRegions& R, std::vector<double>& xs) {
+  const double lo[5] = {0, 1, 5, 25, 150}, hi[5] = {1, 5, 25, 150, (double)kmaxfile};
+  const double dl[5] = {0.01, 0.1, 0.2, 0.5 / boost, 0.8 / boost};
+  R.count = 0;
+  int start = 1;
+  xs.clear();
+  for (int r = 0; r < 5; r++) {
+    if (hi[r] <= lo[r]) break;
+    const double span = hi[r] - lo[r];
+    const int n = std::max(1, (int)(span / dl[r] + 1.0 - 0.1));
+    const double d0 = span / n;                       // Ranges_Add: delta = (t_end - t_start)/nstep
+    const int steps = std::max(1, (int)(span / d0 + 1.0 - 0.1));
+    GcRegion& A = R.R[R.count++];
+    A.Low = lo[r];
+    A.High = hi[r];
+    A.delta = span / steps;
+    A.start_index = start;
+    A.IsLog = 0;
+    for (int j = 0; j < steps; j++) xs.push_back(A.Low + A.delta * j);
+    start += steps;
+  }
+  R.Lowest = 0;
+  R.Highest = R.R[R.count - 1].High;
+  xs.push_back(R.Highest);
+  R.npoints = (int)xs.size();
+}
+
+int grow(double** p, size_t* cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  if (cudaMalloc((void**)p, need * sizeof(double)) != cudaSuccess) return 1;
+  *cap = need;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* galcamb_last_error_(void) { return g.err.c_str(); }
+int galcamb_sizeof_model_(void) { return (int)sizeof(galcamb_model); }
+
+int galcamb_init_(const int* device) {
+  if (g.ready) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(100, "galcamb_init_: no CUDA device (this library has no CPU fallback)");
+  g.device = device ? *device : 0;
+  CK(cudaSetDevice(g.device));
+  CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  for (auto& e : g.ev) CK(cudaEventCreate(&e));
+  gc_upload_constants();
+  CK(cudaMalloc((void**)&g.d_counters, 8 * sizeof(unsigned long long)));
+  CK(cudaMalloc((void**)&g.d_nu_tab, (size_t)GC_NRHOPN * 6 * sizeof(double)));
+  CK(cudaDeviceSetLimit(cudaLimitStackSize, 8192));
+  g.ready = true;
+  return 0;
+}
+
+void galcamb_free_(void) {
+  if (!g.ready) return;
+  cudaSetDevice(g.device);
+  cudaStreamSynchronize(g.stream);
+  for (auto& s : g.slots) {
+    if (s.d_tables) cudaFree(s.d_tables);
+    if (s.d_out) cudaFree(s.d_out);
+  }
+  g.slots.clear();
+  for (void* p : {(void*)g.d_ls, (void*)g.d_xs, (void*)g.d_bess, (void*)g.d_tmpl, (void*)g.d_nu_tab, (void*)g.d_models,
+                  (void*)g.d_items, (void*)g.d_status, (void*)g.d_ws, (void*)g.d_counters})
+    if (p) cudaFree(p);
+  for (auto& e : g.ev) cudaEventDestroy(e);
+  cudaStreamDestroy(g.stream);
+  g = Ctx();
+}
+
+int galcamb_sync_(void) {
+  if (!g.ready) return fail(100, "not initialised");
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int galcamb_set_bessels_(const int* ls, const int* nl, const int* kmaxfile, const double* AccuracyBoost) {
+  if (!g.ready) return fail(100, "not initialised");
+  CK(cudaSetDevice(g.device));
+  const int n = *nl;
+  // cache test of InitSpherBessels, camb/bessels.f90:40-41
+  if (g.d_bess && n <= g.nl && *kmaxfile <= g.kmaxfile && g.bess_boost == *AccuracyBoost &&
+      std::equal(ls, ls + n, g.ls.begin()) && n == g.nl)
+    return 0;
+  CK(cudaEventRecord(g.ev[8], g.stream));
+  GcRegions R{};
+  build_bess_ranges(*kmaxfile, *AccuracyBoost, R, g.xs);
+  g.ls.assign(ls, ls + n);
+  g.nl = n;
+  g.nx = (int)g.xs.size();
+  g.kmaxfile = *kmaxfile;
+  g.bess_boost = *AccuracyBoost;
+  for (void* p : {(void*)g.d_ls, (void*)g.d_xs, (void*)g.d_bess})
+    if (p) cudaFree(p);
+  CK(cudaMalloc((void**)&g.d_ls, n * sizeof(int)));
+  CK(cudaMalloc((void**)&g.d_xs, g.nx * sizeof(double)));
+  CK(cudaMalloc((void**)&g.d_bess, (size_t)g.nx * n * sizeof(double2)));
+  double* scratch = nullptr;
+  CK(cudaMalloc((void**)&scratch, (size_t)g.nx * n * sizeof(double)));
+  CK(cudaMemcpyAsync(g.d_ls, ls, n * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(g.d_xs, g.xs.data(), g.nx * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CK(gc_set_bess_regions(&R));
+  CK(gc_launch_bessels(g.d_bess, g.d_xs, g.d_ls, scratch, g.nx, n, g.stream));
+  CK(cudaEventRecord(g.ev[9], g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  cudaFree(scratch);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, g.ev[8], g.ev[9]);
+  g.ms[6] = ms;
+  return 0;
+}
+
+// debugging / tests: copy the Bessel x grid and tables back (ajl, ajlpr as [nl][nx])
+int galcamb_get_bessels_(int* nx, double* xs, double* ajl, double* ajlpr) {
+  if (!g.d_bess) return fail(100, "no Bessel table");
+  *nx = g.nx;
+  if (xs) std::copy(g.xs.begin(), g.xs.end(), xs);
+  if (ajl || ajlpr) {
+    std::vector<double2> h((size_t)g.nx * g.nl);
+    CK(cudaMemcpy(h.data(), g.d_bess, h.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < h.size(); i++) {
+      if (ajl) ajl[i] = h[i].x;
+      if (ajlpr) ajlpr[i] = h[i].y;
+    }
+  }
+  return 0;
+}
+
+int galcamb_set_template_(const double* tmpl, const int* lmax_tmpl) {
+  if (!g.ready) return fail(100, "not initialised");
+  CK(cudaSetDevice(g.device));
+  if (g.d_tmpl) cudaFree(g.d_tmpl);
+  g.d_tmpl = nullptr;
+  g.lmax_tmpl = 0;
+  if (!tmpl || *lmax_tmpl < 2) return 0;
+  const size_t n = (size_t)3 * (*lmax_tmpl - 1);
+  CK(cudaMalloc((void**)&g.d_tmpl, n * sizeof(double)));
+  CK(cudaMemcpy(g.d_tmpl, tmpl, n * sizeof(double), cudaMemcpyHostToDevice));
+  g.lmax_tmpl = *lmax_tmpl;
+  return 0;
+}
+
+int galcamb_batch_begin_(const int* nmodels) {
+  if (!g.ready) return fail(100, "not initialised");
+  if (*nmodels < 1) return fail(5, "nmodels < 1");
+  if ((int)g.slots.size() < *nmodels) g.slots.resize(*nmodels);
+  for (auto& s : g.slots) s.set = false;
+  g.items.clear();
+  // only the first nmodels slots take part
+  g.slots.resize(*nmodels);
+  return 0;
+}
+
+int galcamb_set_model_(const int* slot, const galcamb_model* m) {
+  if (!g.ready) return fail(100, "not initialised");
+  if (*slot < 0 || *slot >= (int)g.slots.size()) return fail(5, "bad slot");
+  if (g.nl == 0) return fail(5, "galcamb_set_bessels_ must be called first");
+  if (m->Nu_mass_eigenstates > GC_MAX_NU || m->nqmax > GC_MAX_NQ) return fail(5, "too many neutrino eigenstates / q nodes");
+  if (m->n_tau_regions > GC_MAX_REGIONS) return fail(5, "too many TimeSteps regions");
+  CK(cudaSetDevice(g.device));
+  Slot& s = g.slots[*slot];
+  DevModel& D = s.host;
+  D = DevModel{};
+  D.grhom = m->grhom; D.grhog = m->grhog; D.grhor = m->grhor; D.grhob = m->grhob; D.grhoc = m->grhoc; D.grhov = m->grhov;
+  D.grhornomass = m->grhornomass; D.grhok = m->grhok; D.adotrad = m->adotrad; D.tau0 = m->tau0; D.taurst = m->taurst;
+  D.taurend = m->taurend; D.tau_maxvis = m->tau_maxvis; D.tight_tau = m->tight_tau;
+  D.matter_verydom_tau = m->matter_verydom_tau; D.epsw = m->epsw; D.max_etak_scalar = m->max_etak_scalar;
+  D.AccuracyBoost = m->AccuracyBoost; D.lAccuracyBoost = m->lAccuracyBoost;
+  D.tol1 = 1.0e-4 / std::exp(m->AccuracyBoost - 1);  // camb/cmbmain.f90:1019
+  D.use_galileon = m->use_galileon; D.DoLateRadTruncation = m->DoLateRadTruncation;
+  D.HighAccuracyDefault = m->HighAccuracyDefault; D.AccuratePolarization = m->AccuratePolarization;
+  D.AccurateReionization = m->AccurateReionization; D.WantLateTime = m->WantLateTime;
+  D.SourceNum = m->WantLateTime ? 3 : 2;  // GetSourceMem, camb/cmbmain.f90:691-710
+  D.NuMethod = m->MassiveNuMethod == 3 ? 1 : m->MassiveNuMethod;  // Nu_best -> Nu_trunc, equations_galileon.f90:820-821
+  D.n_eig = m->Nu_mass_eigenstates; D.Num_Nu_massive = m->Num_Nu_massive; D.nqmax = m->nqmax;
+  for (int i = 0; i < GC_MAX_NU; i++) {
+    D.grhormass[i] = m->grhormass[i]; D.nu_masses[i] = m->nu_masses[i];
+    D.nu_tau_nonrelativistic[i] = m->nu_tau_nonrelativistic[i]; D.nu_tau_massive[i] = m->nu_tau_massive[i];
+    for (int qn = 0; qn < GC_MAX_NQ; qn++) D.nu_tau_notmassless[qn][i] = m->nu_tau_notmassless[qn][i];
+  }
+  for (int qn = 0; qn < GC_MAX_NQ; qn++) { D.nu_q[qn] = m->nu_q[qn]; D.nu_int_kernel[qn] = m->nu_int_kernel[qn]; }
+  D.dlnam = m->dlnam;
+  if (m->Num_Nu_massive != 0 && !g.nu_tab_set) {
+    if (!m->nu_r1) return fail(5, "massive neutrinos without tables");
+    std::vector<double> t((size_t)GC_NRHOPN * 6);
+    for (int i = 0; i < GC_NRHOPN; i++) {
+      t[i * 6 + 0] = m->nu_r1[i]; t[i * 6 + 1] = m->nu_dr1[i]; t[i * 6 + 2] = m->nu_p1[i];
+      t[i * 6 + 3] = m->nu_dp1[i]; t[i * 6 + 4] = m->nu_ddr1[i]; t[i * 6 + 5] = m->nu_ddp1[i];
+    }
+    CK(cudaMemcpy(g.d_nu_tab, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    g.nu_tab_set = true;
+  }
+  D.nu_tab = g.d_nu_tab;
+  D.nthermo = m->nthermo; D.tauminn = m->tauminn; D.dlntau = m->dlntau;
+  D.nt = m->nt; D.nk = m->nk; D.nq = m->nq;
+  D.c2 = m->c2; D.c3 = m->c3; D.c4 = m->c4; D.c5 = m->c5; D.cG = m->cG; D.h0 = m->h0; D.orad = m->orad;
+  D.ScalarPowerAmp = m->ScalarPowerAmp; D.an = m->an; D.n_run = m->n_run; D.n_runrun = m->n_runrun; D.k_0_scalar = m->k_0_scalar;
+  D.TimeSteps.count = m->n_tau_regions;
+  D.TimeSteps.npoints = m->nt;
+  D.TimeSteps.Lowest = m->tau[0];
+  D.TimeSteps.Highest = m->tau[m->nt - 1];
+  for (int i = 0; i < m->n_tau_regions; i++) {
+    D.TimeSteps.R[i].Low = m->tau_regions[i].Low; D.TimeSteps.R[i].High = m->tau_regions[i].High;
+    D.TimeSteps.R[i].delta = m->tau_regions[i].delta; D.TimeSteps.R[i].start_index = m->tau_regions[i].start_index;
+    D.TimeSteps.R[i].IsLog = m->tau_regions[i].IsLog;
+  }
+  s.lmax = m->lmax;
+  s.ntype = D.SourceNum > 2 ? 6 : 3;
+  // ---- pack the tables
+  const int ngal = m->use_galileon ? m->ngal + 1 : 0;  // + the linearly extrapolated node of galileon.cc:677-679
+  D.ngal = ngal;
+  const size_t n_th = (size_t)m->nthermo * 5, n_pm = m->nthermo, n_ts = (size_t)m->nt * 8, n_gal = (size_t)ngal * 5;
+  const size_t total = n_th + n_pm + n_ts + n_gal + m->nk + 2 * (size_t)m->nq;
+  std::vector<double>& h = s.staging;
+  h.resize(total);
+  double* p = h.data();
+  for (int i = 0; i < m->nthermo; i++) {
+    p[i * 5 + 0] = m->cs2[i]; p[i * 5 + 1] = m->dcs2[i]; p[i * 5 + 2] = m->dotmu[i];
+    p[i * 5 + 3] = m->ddotmu[i]; p[i * 5 + 4] = m->dddotmu[i];
+  }
+  p += n_th;
+  {
+    double mn = m->dotmu[0];
+    for (int i = 0; i < m->nthermo; i++) { mn = std::min(mn, m->dotmu[i]); p[i] = mn; }
+  }
+  p += n_pm;
+  for (int i = 0; i < m->nt; i++) {
+    p[i * 8 + 0] = m->tau[i]; p[i * 8 + 1] = m->dtau[i]; p[i * 8 + 2] = m->vis[i]; p[i * 8 + 3] = m->dvis[i];
+    p[i * 8 + 4] = m->ddvis[i]; p[i * 8 + 5] = m->expmmu[i]; p[i * 8 + 6] = m->opac[i]; p[i * 8 + 7] = m->dopac[i];
+  }
+  p += n_ts;
+  if (ngal) {
+    const int nb1 = m->ngal;  // nb+1 tabulated points, ascending a
+    std::vector<double> a(ngal), hh(ngal), xx(ngal), ch, cx;
+    for (int i = 0; i < nb1; i++) { a[i] = m->gal_a[i]; hh[i] = m->gal_h[i]; xx[i] = m->gal_x[i]; }
+    // galileon.cc:677: intvar_interp[nb+1] = 1./q with q the geometric ratio; a[nb] = 1 so q = a[nb-1] exactly
+    a[nb1] = 1. / (a[nb1 - 2] / a[nb1 - 1]);
+    hh[nb1] = (hh[nb1 - 1] - hh[nb1 - 2]) / (a[nb1 - 1] - a[nb1 - 2]) * (a[nb1] - a[nb1 - 2]) + hh[nb1 - 2];
+    xx[nb1] = (xx[nb1 - 1] - xx[nb1 - 2]) / (a[nb1 - 1] - a[nb1 - 2]) * (a[nb1] - a[nb1 - 2]) + xx[nb1 - 2];
+    natural_spline_c(a, hh, ch);
+    natural_spline_c(a, xx, cx);
+    for (int i = 0; i < ngal; i++) {
+      p[i * 5 + 0] = a[i]; p[i * 5 + 1] = hh[i]; p[i * 5 + 2] = ch[i]; p[i * 5 + 3] = xx[i]; p[i * 5 + 4] = cx[i];
+    }
+    D.gal_a0 = a[0];
+    D.gal_lnq_inv = (nb1 - 1) / std::log(a[nb1 - 1] / a[0]);
+  }
+  p += n_gal;
+  std::copy(m->k, m->k + m->nk, p); p += m->nk;
+  std::copy(m->q, m->q + m->nq, p); p += m->nq;
+  std::copy(m->dq, m->dq + m->nq, p); p += m->nq;
+  if (grow(&s.d_tables, &s.tables_cap, total)) return fail(100, "cudaMalloc tables");
+  CK(cudaMemcpyAsync(s.d_tables, h.data(), total * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  double* d = s.d_tables;
+  D.th = d; d += n_th;
+  D.dotmu_pmin = d; d += n_pm;
+  D.ts = d; d += n_ts;
+  D.gal = d; d += n_gal;
+  D.k = d; d += m->nk;
+  D.q = d; d += m->nq;
+  D.dq = d; d += m->nq;
+  // ---- outputs
+  const size_t n_src = (size_t)m->nk * D.SourceNum * m->nt, n_delta = (size_t)D.SourceNum * g.nl * m->nq;
+  const size_t n_icl = (size_t)s.ntype * g.nl, n_cl = (size_t)s.ntype * (m->lmax - 1);
+  if (grow(&s.d_out, &s.out_cap, 2 * n_src + n_delta + n_icl + n_cl)) return fail(100, "cudaMalloc outputs");
+  d = s.d_out;
+  D.Src = d; d += n_src;
+  D.ddSrc = d; d += n_src;
+  D.Delta = d; d += n_delta;
+  D.iCl = d; d += n_icl;
+  D.Cl = d; d += n_cl;
+  s.set = true;
+  s.status = 0;
+  return 0;
+}
+
+static int upload_models() {
+  const size_t n = g.slots.size();
+  for (auto& s : g.slots)
+    if (!s.set) return fail(5, "a slot of the batch has no model");
+  if (n > g.models_cap) {
+    if (g.d_models) cudaFree(g.d_models);
+    CK(cudaMalloc((void**)&g.d_models, n * sizeof(DevModel)));
+    g.models_cap = n;
+  }
+  std::vector<DevModel> hm(n);
+  for (size_t i = 0; i < n; i++) hm[i] = g.slots[i].host;
+  CK(cudaMemcpyAsync(g.d_models, hm.data(), n * sizeof(DevModel), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaStreamSynchronize(g.stream));  // hm is a local
+  return 0;
+}
+
+int galcamb_evolve_sources_(void) {
+  if (!g.ready) return fail(100, "not initialised");
+  CK(cudaSetDevice(g.device));
+  if (int rc = upload_models()) return rc;
+  const int nm = (int)g.slots.size();
+  // work items ordered by (k index descending, model): with >= 32 models a warp holds the same k index of 32
+  // cosmologies (lock-step control flow); expensive high-k items start first.
+  int max_nk = 0, NV = 0;
+  for (auto& s : g.slots) {
+    max_nk = std::max(max_nk, s.host.nk);
+    const DevModel& D = s.host;
+    const double lAB = D.lAccuracyBoost;
+    int lmaxg = std::max((int)std::lround(11 * lAB), 3);
+    if (D.AccurateReionization) lmaxg = std::max(lmaxg, 4 * std::max(3, (int)std::lround(8 * lAB)));
+    int lmaxgpol = std::max(lmaxg, 2 * std::max(3, (int)std::lround(8 * lAB)));
+    lmaxgpol = std::min(lmaxgpol, std::max((int)std::lround(11 * lAB), 2 * std::max(3, (int)std::lround(8 * lAB))));
+    double mx = 0;
+    for (int i = 0; i < D.n_eig; i++) mx = std::max(mx, D.nu_masses[i]);
+    const int lmaxnr = std::max((int)std::lround((mx > 700 ? 32 : 14) * lAB), 3);
+    const int lmaxnu = D.Num_Nu_massive ? std::max(3, (int)std::lround((mx > 700 ? 15 : 10) * lAB)) : 0;
+    int nv = 5 + (lmaxg + 1) + (lmaxnr + 1) + lmaxgpol - 1 + 2;
+    if (D.Num_Nu_massive) nv += (lmaxnu + 1) + D.n_eig * D.nqmax * (lmaxnu + 1);
+    NV = std::max(NV, nv);
+  }
+  g.items.clear();
+  for (int kk = max_nk - 1; kk >= 0; kk--)
+    for (int m = 0; m < nm; m++)
+      if (kk < g.slots[m].host.nk) g.items.push_back(make_int2(m, kk));
+  const int nitems = (int)g.items.size();
+  if ((size_t)nitems > g.items_cap) {
+    if (g.d_items) cudaFree(g.d_items);
+    if (g.d_status) cudaFree(g.d_status);
+    CK(cudaMalloc((void**)&g.d_items, nitems * sizeof(int2)));
+    CK(cudaMalloc((void**)&g.d_status, nitems * sizeof(int)));
+    g.items_cap = nitems;
+  }
+  const size_t nwarps = (nitems + 31) / 32;
+  const size_t ws_need = nwarps * 10 * (size_t)NV * 32;
+  if (grow(&g.d_ws, &g.ws_cap, ws_need)) return fail(100, "cudaMalloc workspace");
+  CK(cudaMemcpyAsync(g.d_items, g.items.data(), nitems * sizeof(int2), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemsetAsync(g.d_counters, 0, 8 * sizeof(unsigned long long), g.stream));
+  CK(cudaEventRecord(g.ev[0], g.stream));
+  CK(gc_launch_evolve(g.d_models, g.d_items, nitems, g.d_ws, NV, g.d_status, g.d_counters, g.stream));
+  CK(cudaEventRecord(g.ev[1], g.stream));
+  std::vector<int> st(nitems);
+  CK(cudaMemcpyAsync(st.data(), g.d_status, nitems * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  unsigned long long c[4];
+  CK(cudaMemcpyAsync(c, g.d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]);
+  g.ms[0] = ms;
+  g.counters[0] = (double)c[0];
+  g.counters[1] = (double)c[1];
+  g.counters[2] = (double)c[2];
+  int rc = 0;
+  for (int i = 0; i < nitems; i++)
+    if (st[i]) {
+      g.slots[g.items[i].x].status = st[i] >= 100 ? 4 : st[i];
+      rc = 4;  // error_evolution
+      char buf[160];
+      snprintf(buf, sizeof buf, "evolve_sources: status %d for model %d k index %d", st[i], g.items[i].x, g.items[i].y);
+      g.err = buf;
+    }
+  return rc;
+}
+
+int galcamb_los_integrate_(void) {
+  if (!g.ready) return fail(100, "not initialised");
+  CK(cudaSetDevice(g.device));
+  if (int rc = upload_models()) return rc;
+  const int nm = (int)g.slots.size();
+  int max_rows = 0, max_nq = 0, max_nt = 0, S = 2;
+  for (auto& s : g.slots) {
+    max_rows = std::max(max_rows, s.host.nt * s.host.SourceNum);
+    max_nq = std::max(max_nq, s.host.nq);
+    max_nt = std::max(max_nt, s.host.nt);
+    S = std::max(S, s.host.SourceNum);
+    if (s.host.nk > 768) return fail(5, "nk > 768 not supported by spline_k");
+  }
+  CK(cudaEventRecord(g.ev[2], g.stream));
+  CK(gc_launch_spline_k(g.d_models, nm, max_rows, g.stream));
+  CK(cudaEventRecord(g.ev[3], g.stream));
+  for (auto& s : g.slots) CK(gc_launch_zero(s.host.Delta, (size_t)s.host.SourceNum * g.nl * s.host.nq, g.stream));
+  CK(cudaMemsetAsync(g.d_counters + 3, 0, sizeof(unsigned long long), g.stream));
+  CK(gc_launch_los(g.d_models, nm, max_nq, max_nt, S, g.d_bess, g.d_xs, g.d_ls, g.nx, g.nl, g.d_counters + 3, g.stream));
+  CK(cudaEventRecord(g.ev[4], g.stream));
+  unsigned long long c = 0;
+  CK(cudaMemcpyAsync(&c, g.d_counters + 3, sizeof c, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, g.ev[2], g.ev[3]);
+  g.ms[1] = ms;
+  cudaEventElapsedTime(&ms, g.ev[3], g.ev[4]);
+  g.ms[2] = ms;
+  g.counters[3] = (double)c;
+  return 0;
+}
+
+int galcamb_scalar_cls_(void) {
+  if (!g.ready) return fail(100, "not initialised");
+  CK(cudaSetDevice(g.device));
+  if (int rc = upload_models()) return rc;
+  const int nm = (int)g.slots.size();
+  const int lmax = g.slots[0].lmax, ntype = g.slots[0].ntype;
+  for (auto& s : g.slots)
+    if (s.lmax != lmax || s.ntype != ntype) return fail(5, "all models of a batch must share lmax and source count");
+  if (g.nl > 512) return fail(5, "nl > 512 not supported");
+  CK(cudaEventRecord(g.ev[5], g.stream));
+  CK(gc_launch_cls(g.d_models, nm, g.d_ls, g.nl, ntype, lmax, g.d_tmpl, g.lmax_tmpl, g.stream));
+  CK(cudaEventRecord(g.ev[6], g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, g.ev[5], g.ev[6]);
+  g.ms[3] = ms;
+  return 0;
+}
+
+int galcamb_get_sources_(const int* slot, double* Src) {
+  if (*slot < 0 || *slot >= (int)g.slots.size() || !g.slots[*slot].set) return fail(5, "bad slot");
+  const DevModel& D = g.slots[*slot].host;
+  CK(cudaMemcpyAsync(Src, D.Src, (size_t)D.nk * D.SourceNum * D.nt * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int galcamb_put_sources_(const int* slot, const double* Src) {
+  if (*slot < 0 || *slot >= (int)g.slots.size() || !g.slots[*slot].set) return fail(5, "bad slot");
+  const DevModel& D = g.slots[*slot].host;
+  CK(cudaMemcpyAsync(D.Src, Src, (size_t)D.nk * D.SourceNum * D.nt * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int galcamb_get_transfers_(const int* slot, double* Delta) {
+  if (*slot < 0 || *slot >= (int)g.slots.size() || !g.slots[*slot].set) return fail(5, "bad slot");
+  const DevModel& D = g.slots[*slot].host;
+  CK(cudaMemcpyAsync(Delta, D.Delta, (size_t)D.SourceNum * g.nl * D.nq * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int galcamb_get_cls_(const int* slot, double* iCl, double* Cl) {
+  if (*slot < 0 || *slot >= (int)g.slots.size() || !g.slots[*slot].set) return fail(5, "bad slot");
+  const Slot& s = g.slots[*slot];
+  if (iCl) CK(cudaMemcpyAsync(iCl, s.host.iCl, (size_t)s.ntype * g.nl * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  if (Cl) CK(cudaMemcpyAsync(Cl, s.host.Cl, (size_t)s.ntype * (s.lmax - 1) * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int galcamb_get_status_(const int* slot, int* status) {
+  if (*slot < 0 || *slot >= (int)g.slots.size()) return fail(5, "bad slot");
+  *status = g.slots[*slot].status;
+  return 0;
+}
+
+int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* Cl_out) {
+  if (!g.ready) return fail(100, "not initialised");
+  int rc = galcamb_batch_begin_(nmodels);
+  if (rc) return rc;
+  for (int i = 0; i < *nmodels; i++)
+    if ((rc = galcamb_set_model_(&i, &models[i]))) return rc;
+  if ((rc = galcamb_evolve_sources_())) return rc;
+  if ((rc = galcamb_los_integrate_())) return rc;
+  if ((rc = galcamb_scalar_cls_())) return rc;
+  const size_t per = (size_t)3 * (models[0].lmax - 1);
+  for (int i = 0; i < *nmodels; i++)
+    CK(cudaMemcpyAsync(Cl_out + per * i, g.slots[i].host.Cl, per * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int galcamb_get_timings_(double* ms) {
+  for (int i = 0; i < 8; i++) ms[i] = g.ms[i];
+  ms[7] = g.ms[0] + g.ms[1] + g.ms[2] + g.ms[3];
+  return 0;
+}
+
+int galcamb_get_counters_(double* c) {
+  for (int i = 0; i < 4; i++) c[i] = g.counters[i];
+  return 0;
+}
+
+}  // extern "C"

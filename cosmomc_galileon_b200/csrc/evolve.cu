@@ -1,0 +1,521 @@
+// K1 "evolve_sources": per-(k, cosmology) integration of the Einstein-Boltzmann + Galileon system with the
+// Verner 6(5) pair of dverk, sampling the CMB sources on the output time grid.
+//
+// Replaces the OpenMP loop camb/cmbmain.f90:201-206 (DoSourcek :662 -> CalcScalarSources :917 ->
+// GaugeInterface_EvolveScal camb/equations_galileon.f90:314 -> dverk camb/subroutines.f90:370 -> derivs/output).
+//
+// Execution model (DESIGN.md "K1"): one lane per (k, cosmology) work item, FP64 throughout.  Each lane runs the
+// reference's control flow (output-time loop, approximation switches, adaptive step accept/reject) as an explicit
+// state machine that stops whenever it needs a right-hand-side evaluation; the warp then executes ONE converged
+// call of derivs() for all of its lanes.  Lanes of a warp therefore share the ~2 kFLOP RHS instruction stream
+// even when they sit in different Runge-Kutta stages, at different step sizes or in different output intervals;
+// only the short bookkeeping between evaluations diverges.
+#include <cstdio>
+
+#include "evolve_device.cuh"
+
+namespace gc {
+
+enum Phase : int {
+  PH_NEXT_OUTPUT = 0,
+  PH_EVOLVE,
+  PH_DO_SWITCH,
+  PH_DV_ENTER,
+  PH_DV_LOOP,
+  PH_DV_K1,
+  PH_DV_STAGE,
+  PH_OUT_REQ,
+  PH_OUT_DONE,
+  PH_DONE
+};
+
+struct Lane {
+  EV e;
+  const DevModel* M;
+  double* ws;  // lane base of the warp workspace
+  int NV;
+  int kidx;
+  int phase, stage, j, ind, after_switch;
+  bool evaluated;
+  double tau, tauend, target;
+  // dverk communication (c(13), c(14), c(17), c(18), c(19), c(20), c(21), c(23))
+  double hmin, hmag, xtrial, htrial, est, c20, c21, nfail;
+  // pending RHS request
+  double req_tau;
+  int req_in, req_out;
+  int status;
+  // work counters
+  unsigned long long n_derivs, sum_n, n_out;
+};
+
+__device__ __forceinline__ double* col(const Lane& L, int c) { return L.ws + (size_t)c * L.NV * GC_LANES; }
+
+// Verner 6(5) stage tableau of camb/subroutines.f90:930-993: w9 = y + temp*(sum_j A[s][j]*w_j), evaluated left to
+// right with the reference's signs so that every partial sum is bit-identical to the Fortran expression.
+__constant__ double c_A[7][7] = {
+    {233028180000.0, 0, 0, 0, 0, 0, 0},
+    {74569017600.0, 298276070400.0, 0, 0, 0, 0, 0},
+    {1165140900000.0, -3728450880000.0, 3495422700000.0, 0, 0, 0, 0},
+    {-3604654659375.0, 12816549900000.0, -9284716546875.0, 1237962206250.0, 0, 0, 0},
+    {3355605792000.0, -11185352640000.0, 9172628850000.0, -427218330000.0, 482505408000.0, 0, 0},
+    {-770204740536.0, 2311639545600.0, -1322092233000.0, -453006781920.0, 326875481856.0, 0, 0},
+    {2845924389000.0, -9754668000000.0, 7897110375000.0, -192082660000.0, 400298976000.0, 0, 201586000000.0}};
+__constant__ int c_Aused[7][7] = {{1, 0, 0, 0, 0, 0, 0}, {1, 1, 0, 0, 0, 0, 0}, {1, 1, 1, 0, 0, 0, 0}, {1, 1, 1, 1, 0, 0, 0},
+                                  {1, 1, 1, 1, 1, 0, 0}, {1, 1, 1, 1, 1, 0, 0}, {1, 1, 1, 1, 1, 0, 1}};
+
+struct Switches {
+  double ktau, no_nu, no_phot, nu_massless, nu_nonrel, nu_massive, next;
+};
+
+// camb/equations_galileon.f90:328-364
+__device__ inline void compute_switches(const Lane& L, Switches& s) {
+  const DevModel& M = *L.M;
+  const EV& e = L.e;
+  const double noSwitch = M.tau0 + 1;
+  s.ktau = s.no_nu = s.no_phot = s.nu_massless = s.nu_nonrel = s.nu_massive = noSwitch;
+  if (!e.high_ktau && !e.no_nu) s.ktau = max(20, e.lmaxnr - 4) / e.k;
+  if (M.Num_Nu_massive != 0) {
+    for (int nu_i = 0; nu_i < M.n_eig; nu_i++) {
+      if (e.nq[nu_i] != M.nqmax)
+        s.nu_massless = fmin(s.nu_massless, M.nu_tau_notmassless[next_nu_nq(M, e.nq[nu_i]) - 1][nu_i]);
+      else if (!e.nu_nonrel[nu_i])
+        s.nu_nonrel = fmin(M.nu_tau_nonrelativistic[nu_i], s.nu_nonrel);
+      else if (M.NuMethod == 1 && !e.MassiveNuApprox[nu_i])
+        s.nu_massive = fmin(s.nu_massive, e.MassiveNuApproxTime[nu_i]);
+    }
+  }
+  if (M.DoLateRadTruncation) {
+    if (!e.no_nu) s.no_nu = fmax(15 / e.k * M.AccuracyBoost, fmin(M.taurend, M.matter_verydom_tau));
+    if (!e.no_phot && (e.k > GC_SP(0.03) * M.AccuracyBoost)) s.no_phot = fmax(15 / e.k, M.taurend) * M.AccuracyBoost;
+  }
+  double n = fmin(s.ktau, s.nu_massless);
+  n = fmin(n, e.TightSwitchoffTime);
+  n = fmin(n, s.nu_massive);
+  n = fmin(n, s.no_nu);
+  n = fmin(n, s.no_phot);
+  n = fmin(n, s.nu_nonrel);
+  n = fmin(n, noSwitch);
+  s.next = n;
+}
+
+// the switch bodies of camb/equations_galileon.f90:370-463 (y in column 0, scratch column 9)
+__device__ inline void do_switch(Lane& L) {
+  const DevModel& M = *L.M;
+  EV& e = L.e;
+  Switches s;
+  compute_switches(L, s);
+  const double next_switch = s.next;
+  const double noSwitch = M.tau0 + 1;
+  double* y = col(L, 0);
+  double* yout = col(L, 9);
+  EV o = e;
+  bool relayout = false;
+  bool tight = false;
+  if (next_switch == e.TightSwitchoffTime) {
+    o.TightCoupling = false;
+    o.TightSwitchoffTime = noSwitch;
+    relayout = true;
+    tight = true;
+    L.ind = 1;
+  } else if (next_switch == s.ktau) {
+    o.high_ktau = true;
+    relayout = true;
+  } else if (next_switch == s.nu_massless) {
+    for (int nu_i = 0; nu_i < M.n_eig; nu_i++) {
+      if (e.nq[nu_i] != M.nqmax && next_switch == M.nu_tau_notmassless[next_nu_nq(M, e.nq[nu_i]) - 1][nu_i]) {
+        o.nq[nu_i] = next_nu_nq(M, e.nq[nu_i]);
+        relayout = true;
+        break;
+      }
+    }
+  } else if (next_switch == s.nu_nonrel) {
+    for (int nu_i = 0; nu_i < M.n_eig; nu_i++) {
+      if (!e.nu_nonrel[nu_i] && next_switch == M.nu_tau_nonrelativistic[nu_i]) {
+        o.nu_nonrel[nu_i] = true;
+        relayout = true;
+        break;
+      }
+    }
+  } else if (next_switch == s.nu_massive) {
+    for (int nu_i = 0; nu_i < M.n_eig; nu_i++) {
+      if (!e.MassiveNuApprox[nu_i] && next_switch == e.MassiveNuApproxTime[nu_i]) {
+        // SwitchToMassiveNuApprox, :949-990
+        const double a = AT(y, 1), a2 = a * a;
+        o.MassiveNuApprox[nu_i] = true;
+        SetupScalarArrayIndices(M, o, nullptr);
+        CopyScalarVariableArray(M, y, yout, e, o);
+        double rhonu, pnu, clxnu, qnu, dpnu, pinu;
+        Nu_background(M, a * M.nu_masses[nu_i], rhonu, pnu);
+        Nu_Integrate_L012(M, e, y, a, nu_i, clxnu, qnu, &dpnu, &pinu);
+        dpnu = dpnu / rhonu;
+        qnu = qnu / rhonu;
+        clxnu = clxnu / rhonu;
+        pinu = pinu / rhonu;
+        AT(yout, o.nu_ix[nu_i]) = clxnu;
+        AT(yout, o.nu_ix[nu_i] + 1) = dpnu;
+        AT(yout, o.nu_ix[nu_i] + 2) = qnu;
+        AT(yout, o.nu_ix[nu_i] + 3) = pinu;
+        Nu_Intvsq(M, e, y, a, nu_i, o.G11[nu_i], o.G30[nu_i]);
+        o.G11[nu_i] = o.G11[nu_i] * a2 * a / rhonu;
+        o.G30[nu_i] = o.G30[nu_i] * a2 * a / rhonu;
+        e = o;
+        for (int i = 1; i <= e.nvar; i++) AT(y, i) = AT(yout, i);
+        break;
+      }
+    }
+  } else if (next_switch == s.no_nu) {
+    L.ind = 1;
+    o.no_nu = true;
+    for (int i = 0; i < M.n_eig; i++) o.nq[i] = M.nqmax;
+    relayout = true;
+  } else if (next_switch == s.no_phot) {
+    L.ind = 1;
+    o.no_phot = true;
+    relayout = true;
+  }
+  if (relayout) {
+    SetupScalarArrayIndices(M, o, nullptr);
+    CopyScalarVariableArray(M, y, yout, e, o);
+    e = o;
+    for (int i = 1; i <= e.nvar; i++) AT(y, i) = AT(yout, i);
+  }
+  if (tight) {
+    AT(y, e.g_ix + 2) = e.pig;
+    double cs2, opacity, dopacity;
+    thermo(M, L.tau, cs2, opacity, &dopacity);
+    const double op2 = opacity * opacity;
+    AT(y, e.g_ix + 3) = (3.0 / 7.0) * AT(y, e.g_ix + 2) * (e.k / opacity) * (1.0 + dopacity / op2) +
+                        (3.0 / 7.0) * e.pigdot * (e.k / op2) * (-1.0);
+    AT(y, e.polind + 2) = e.pig / 4 + e.pigdot * (1.0 / opacity) * (-5.0 / 8.0 - (25.0 / 16.0) * dopacity / op2) +
+                          e.pig * ((e.k / opacity) * (e.k / opacity)) * (-5.0 / 56.0);
+    AT(y, e.polind + 3) = (3.0 / 7.0) * (e.k / opacity) * AT(y, e.polind + 2) * (1.0 + dopacity / op2) +
+                          (3.0 / 7.0) * (e.k / op2) * ((e.pigdot / 4.0) * (1.0 + (5.0 / 2.0) * dopacity / op2)) * (-1.0);
+  }
+}
+
+// Run the lane's control flow until it needs derivs() (returns with L.req_* set) or finishes.
+__device__ __noinline__ void advance(Lane& L) {
+  const DevModel& M = *L.M;
+  EV& e = L.e;
+  const int S = M.SourceNum;
+  const double tol = M.tol1;
+  for (;;) {
+    switch (L.phase) {
+      case PH_NEXT_OUTPUT: {
+        L.j++;
+        if (L.j > M.nt) {
+          L.phase = PH_DONE;
+          return;
+        }
+        const double tauend = M.ts[(size_t)(L.j - 1) * 8];
+        if ((e.q * tauend > M.max_etak_scalar && tauend > M.taurend) && !M.WantLateTime) {
+          // camb/cmbmain.f90:1034-1036
+          for (int s = 0; s < S; s++) M.Src[((size_t)(L.j - 1) * S + s) * M.nk + L.kidx] = 0;
+          break;
+        }
+        L.tauend = tauend;
+        L.phase = PH_EVOLVE;
+        break;
+      }
+      case PH_EVOLVE: {  // camb/equations_galileon.f90:314-469, one pass of the (tail-)recursion
+        Switches s;
+        compute_switches(L, s);
+        const double smallTime = fmin(L.tau, 1 / e.k) / 100;
+        if (s.next < L.tauend) {
+          if (s.next > L.tau + smallTime) {
+            L.target = s.next;
+            L.after_switch = 1;
+            L.phase = PH_DV_ENTER;
+          } else {
+            L.phase = PH_DO_SWITCH;
+          }
+        } else {
+          L.target = L.tauend;
+          L.after_switch = 0;
+          L.phase = PH_DV_ENTER;
+        }
+        break;
+      }
+      case PH_DO_SWITCH: {
+        do_switch(L);
+        L.phase = PH_EVOLVE;
+        break;
+      }
+      case PH_DV_ENTER: {  // camb/subroutines.f90:700-770 (entry logic of dverk)
+        if (L.ind == 3) {
+          if (L.c21 != 0.0 && (L.tau != L.c20 || L.target == L.c20)) {
+            L.status = 101;
+            L.phase = PH_DONE;
+            return;
+          }
+          L.c21 = 0.0;
+        } else {  // ind = 1
+          L.c20 = L.tau;
+          L.c21 = 0.0;
+          L.nfail = 0.0;
+          L.hmag = 0.0;
+          L.est = 0.0;
+        }
+        L.phase = PH_DV_LOOP;
+        break;
+      }
+      case PH_DV_LOOP: {
+        if (L.ind != 6) {
+          L.req_tau = L.tau;
+          L.req_in = 0;
+          L.req_out = 1;
+          L.evaluated = true;
+          L.phase = PH_DV_K1;
+          return;
+        }
+        L.evaluated = false;
+        L.phase = PH_DV_K1;
+        break;
+      }
+      case PH_DV_K1: {  // step-size selection, camb/subroutines.f90:800-925, then stage 2 input
+        const int n = e.neq;
+        const double* y = col(L, 0);
+        const double x = L.tau, xend = L.target;
+        double temp = 0.0;
+        for (int i = 1; i <= n; i++) temp = fmax(temp, fabs(AT(y, i)));
+        const double c12 = fmin(temp, 1.0);
+        L.hmin = 10.0 * fmax(1.e-35, 1.3877787807814457e-17 * fmax(c12 / tol, fabs(x)));  // rreb = 2^-56
+        const double hmax = 2.0;
+        if (L.hmin > hmax) {
+          L.status = 102;
+          L.phase = PH_DONE;
+          return;
+        }
+        if (L.ind <= 2) {
+          L.hmag = hmax * pow(tol, 1.0 / 6.0);
+        } else if (L.nfail <= 1.0) {
+          temp = 2.0 * L.hmag;
+          const double r = 2.0 / .9;
+          if (tol < (r * r * r * r * r * r) * L.est) temp = .9 * pow(tol / L.est, 1.0 / 6.0) * L.hmag;
+          L.hmag = fmax(temp, .5 * L.hmag);
+        } else {
+          L.hmag = .5 * L.hmag;
+        }
+        L.hmag = fmin(L.hmag, hmax);
+        L.hmag = fmax(L.hmag, L.hmin);
+        if (L.hmag >= fabs(xend - x)) {
+          L.hmag = fabs(xend - x);
+          L.xtrial = xend;
+        } else {
+          L.hmag = fmin(L.hmag, .5 * fabs(xend - x));
+          L.xtrial = x + copysign(L.hmag, xend - x);
+        }
+        L.htrial = L.xtrial - x;
+        temp = L.htrial / 1398169080000.0;
+        const double* w1 = col(L, 1);
+        double* w9 = col(L, 9);
+        for (int i = 1; i <= n; i++) AT(w9, i) = AT(y, i) + temp * AT(w1, i) * 233028180000.0;
+        L.req_tau = x + L.htrial / 6.0;
+        L.req_in = 9;
+        L.req_out = 2;
+        L.stage = 2;
+        L.phase = PH_DV_STAGE;
+        return;
+      }
+      case PH_DV_STAGE: {
+        const int n = e.neq;
+        const int s = L.stage;  // the stage whose derivative has just been written (2..8)
+        const double* y = col(L, 0);
+        double* w9 = col(L, 9);
+        const double x = L.tau;
+        const double temp = L.htrial / 1398169080000.0;
+        if (s < 8) {
+          // input of stage s+1 : row s-1 of the tableau
+          const int row = s - 1;
+          for (int i = 1; i <= n; i++) {
+            double acc = AT(col(L, 1), i) * c_A[row][0];
+#pragma unroll
+            for (int jj = 1; jj < 7; jj++)
+              if (c_Aused[row][jj]) acc = acc + AT(col(L, jj + 1), i) * c_A[row][jj];
+            AT(w9, i) = AT(y, i) + temp * acc;
+          }
+          double frac;
+          switch (s) {
+            case 2: frac = 4.0 / 15.0; break;
+            case 3: frac = 2.0 / 3.0; break;
+            case 4: frac = 5.0 / 6.0; break;
+            case 5: frac = 1.0; break;
+            case 6: frac = 1.0 / 15.0; break;
+            default: frac = 1.0; break;
+          }
+          if (s == 5 || s == 7)
+            L.req_tau = x + L.htrial;
+          else if (s == 6)
+            L.req_tau = x + L.htrial / 15.0;
+          else
+            L.req_tau = x + L.htrial * frac;
+          L.req_in = 9;
+          L.req_out = s + 1;
+          L.stage = s + 1;
+          return;
+        }
+        // s == 8: solution, error estimate, accept/reject (camb/subroutines.f90:995-1110)
+        const double *w1 = col(L, 1), *w3 = col(L, 3), *w4 = col(L, 4), *w5 = col(L, 5), *w6 = col(L, 6), *w7 = col(L, 7),
+                     *w8 = col(L, 8);
+        double errn = 0.0;
+        for (int i = 1; i <= n; i++) {
+          AT(w9, i) = AT(y, i) + temp * (AT(w1, i) * 104862681000.0 + AT(w3, i) * 545186250000.0 + AT(w4, i) * 446637345000.0 +
+                                         AT(w5, i) * 188806464000.0 + AT(w7, i) * 15076875000.0 + AT(w8, i) * 97599465000.0);
+          const double w2 = (AT(w1, i) * 8738556750.0 + AT(w3, i) * 9735468750.0 - AT(w4, i) * 9709507500.0 +
+                             AT(w5, i) * 8582112000.0 + AT(w6, i) * 95329710000.0 - AT(w7, i) * 15076875000.0 -
+                             AT(w8, i) * 97599465000.0) /
+                            1398169080000.0;
+          errn = fmax(errn, fabs(w2) / fmax(1.0, fabs(AT(y, i))));
+        }
+        L.est = errn * L.hmag * 1.0;
+        L.ind = 5;
+        if (L.est > tol) L.ind = 6;
+        if (L.ind != 6) {
+          L.tau = L.xtrial;
+          double* yw = col(L, 0);
+          for (int i = 1; i <= n; i++) AT(yw, i) = AT(w9, i);
+          L.nfail = 0.0;
+          if (L.tau == L.target) {
+            L.ind = 3;
+            L.c20 = L.target;
+            L.c21 = 1.0;
+            L.phase = L.after_switch ? PH_DO_SWITCH : PH_OUT_REQ;
+            break;
+          }
+        } else {
+          L.nfail = L.nfail + 1.0;
+          if (!(L.hmag > L.hmin)) {
+            L.status = 4;  // dverk ind=-3 -> error_evolution (camb/equations_galileon.f90:285-292)
+            L.phase = PH_DONE;
+            return;
+          }
+        }
+        L.phase = PH_DV_LOOP;
+        break;
+      }
+      case PH_OUT_REQ: {  // camb/equations_galileon.f90:1296-1297
+        double* yp = col(L, 2);
+        for (int i = 1; i <= e.nvar; i++) AT(yp, i) = 0;
+        L.req_tau = L.tau;
+        L.req_in = 0;
+        L.req_out = 2;
+        L.phase = PH_OUT_DONE;
+        return;
+      }
+      case PH_OUT_DONE: {
+        double src[3] = {0, 0, 0};
+        output_sources(M, e, col(L, 0), col(L, 2), M.ts + (size_t)(L.j - 1) * 8, L.tau, src);
+        for (int s = 0; s < S; s++) M.Src[((size_t)(L.j - 1) * S + s) * M.nk + L.kidx] = src[s];
+        L.n_out++;
+        L.phase = PH_NEXT_OUTPUT;
+        break;
+      }
+      default:
+        return;
+    }
+  }
+}
+
+// items[i] = (model index, k index); workspace = nwarps * GC_NCOL * NV * 32 doubles.
+__global__ void __launch_bounds__(128) evolve_sources_kernel(const DevModel* __restrict__ models, const int2* __restrict__ items,
+                                                             int nitems, double* __restrict__ workspace, int NV,
+                                                             int* __restrict__ status,
+                                                             unsigned long long* __restrict__ counters) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = tid >> 5;
+  const bool have = tid < nitems;
+  Lane L;
+  L.phase = PH_DONE;
+  L.status = 0;
+  L.n_derivs = L.sum_n = L.n_out = 0;
+  if (have) {
+    const int2 it = items[tid];
+    L.M = models + it.x;
+    const DevModel& M = *L.M;
+    L.kidx = it.y;
+    L.NV = NV;
+    L.ws = workspace + (size_t)gwarp * GC_NCOL * NV * GC_LANES + lane;
+    // DoSourcek, camb/cmbmain.f90:662-689
+    L.e.q = M.k[it.y];
+    L.e.pig = 0;
+    L.e.pigdot = 0;
+    for (int i = 0; i < GC_MAX_NU; i++) {
+      L.e.nu_ix[i] = 0;
+      L.e.nq[i] = 0;
+      L.e.lmaxnu_tau[i] = 0;
+      L.e.nu_nonrel[i] = false;
+      L.e.G11[i] = L.e.G30[i] = L.e.MassiveNuApproxTime[i] = 0;
+    }
+    L.e.nu_pert_ix = 0;
+    L.e.lmaxnu_pert = 0;
+    L.e.polind = 0;
+    GetNumEqns(M, L.e);
+    if (L.e.nvar > NV) {
+      L.status = 103;
+    } else {
+      // GetTauStart, camb/cmbmain.f90:634-660
+      double taustart = 0.001 / L.e.q;
+      taustart = fmin(taustart, 0.1);
+      if (M.Num_Nu_massive > 0) {
+        double mx = 0;
+        for (int i = 0; i < M.n_eig; i++) mx = fmax(mx, M.nu_masses[i]);
+        taustart = fmin(taustart, 1.e-3 / mx / M.adotrad);
+      }
+      // w = 0 (camb/cmbmain.f90:946)
+      for (int c = 1; c < GC_NCOL; c++) {
+        double* p = col(L, c);
+        for (int i = 1; i <= L.e.nvar; i++) AT(p, i) = 0;
+      }
+      initial(M, L.e, col(L, 0), taustart);
+      L.tau = taustart;
+      L.ind = 1;
+      L.j = 1;
+      L.c20 = 0;
+      L.c21 = 0;
+      L.nfail = 0;
+      L.hmag = 0;
+      L.est = 0;
+      L.hmin = 0;
+      // Src(:,:,1) = 0 (never written by the time loop, camb/cmbmain.f90:1031)
+      for (int s = 0; s < M.SourceNum; s++) M.Src[(size_t)s * M.nk + L.kidx] = 0;
+      L.phase = PH_NEXT_OUTPUT;
+    }
+  }
+  for (;;) {
+    if (L.phase != PH_DONE) advance(L);
+    const bool need = L.phase != PH_DONE;
+    if (!__any_sync(0xffffffffu, need)) break;
+    if (need) {
+      derivs(*L.M, L.e, L.req_tau, col(L, L.req_in), col(L, L.req_out));
+      L.n_derivs++;
+      L.sum_n += L.e.neq;
+    }
+  }
+  if (have) {
+    status[tid] = L.status;
+    atomicAdd(&counters[0], L.n_derivs);
+    atomicAdd(&counters[1], L.sum_n);
+    atomicAdd(&counters[2], L.n_out);
+  }
+}
+
+}  // namespace gc
+
+extern "C" void gc_upload_constants() {
+  double denl[260], polfac[260];
+  for (int j = 0; j < 260; j++) {
+    denl[j] = 1.0 / (2 * j + 1);
+    polfac[j] = j >= 1 ? (double)((j + 3) * (j - 1)) / (j + 1) : 0.0;
+  }
+  cudaMemcpyToSymbol(c_denl, denl, sizeof(denl));
+  cudaMemcpyToSymbol(c_polfac, polfac, sizeof(polfac));
+}
+
+extern "C" cudaError_t gc_launch_evolve(const DevModel* models, const int2* items, int nitems, double* workspace, int NV,
+                                        int* status, unsigned long long* counters, cudaStream_t stream) {
+  const int threads = 128;
+  const int blocks = (nitems + threads - 1) / threads;
+  gc::evolve_sources_kernel<<<blocks, threads, 0, stream>>>(models, items, nitems, workspace, NV, status, counters);
+  return cudaGetLastError();
+}

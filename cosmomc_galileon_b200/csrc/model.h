@@ -1,0 +1,76 @@
+// Device-side view of one cosmological model (everything the per-k perturbation kernel and the
+// line-of-sight kernels read).  Plain data; built by capi.cu from the caller's galcamb_model.
+//
+// Layout in HBM (one block per model, all float64 unless noted):
+//   th   [nthermo][5]   = {cs2, dcs2, dotmu, ddotmu, dddotmu} rows of the log-tau thermo table (AoS so one
+//                          Hermite lookup touches 2 adjacent 40-byte rows instead of 10 separate arrays;
+//                          reference tables: camb/modules.f90:2705-2713)
+//   ts   [nt][8]        = {tau, dtau, vis, dvis, ddvis, expmmu, opac, dopac} per output time
+//                          (camb/modules.f90:2715, TimeSteps%points/dpoints)
+//   gal  [ngal][5]      = {a, hbar, c_h, x, c_x} rows of the Galileon background spline
+//                          (camb/galileon.cc:666-682; c_* = natural-spline second derivative / 2)
+//   dotmu_pmin [nthermo] = running minimum of dotmu (turns the linear scan of Thermo_OpacityToTime,
+//                          camb/modules.f90:2771-2783, into a bisection with the same answer)
+//   k    [nk]           = source wavenumbers (Evolve_q%points)
+#pragma once
+#include <cstddef>
+
+#define GC_MAX_NU 3      // mass eigenstates handled on the device
+#define GC_MAX_NQ 5      // momentum nodes (nqmax <= 5 for AccuracyBoost <= 3; camb/modules.f90:1624-1627)
+#define GC_NRHOPN 2000   // camb/modules.f90:1554
+#define GC_MAX_REGIONS 16
+
+struct GcRegion {  // camb/utils.F90:8-20 (piecewise linear/log grid)
+  double Low, High, delta;
+  int start_index, IsLog;
+};
+
+struct GcRegions {
+  int count, npoints;
+  double Lowest, Highest;
+  GcRegion R[GC_MAX_REGIONS];
+};
+
+struct DevModel {
+  // densities, times (camb/modules.f90:171-193)
+  double grhom, grhog, grhor, grhob, grhoc, grhov, grhornomass, grhok;
+  double adotrad, tau0, taurst, taurend, tau_maxvis, tight_tau, matter_verydom_tau, epsw;
+  double max_etak_scalar, AccuracyBoost, lAccuracyBoost, tol1;
+  int use_galileon, DoLateRadTruncation, HighAccuracyDefault, AccuratePolarization, AccurateReionization;
+  int WantLateTime, SourceNum, NuMethod;
+  // massive neutrinos
+  int n_eig, Num_Nu_massive, nqmax;
+  double grhormass[GC_MAX_NU], nu_masses[GC_MAX_NU];
+  double nu_q[GC_MAX_NQ], nu_int_kernel[GC_MAX_NQ];
+  double nu_tau_notmassless[GC_MAX_NQ][GC_MAX_NU], nu_tau_nonrelativistic[GC_MAX_NU], nu_tau_massive[GC_MAX_NU];
+  double dlnam;
+  const double* nu_tab;  // [6][GC_NRHOPN] r1,p1,dr1,dp1,ddr1,ddp1 (shared by all models)
+  // thermo
+  int nthermo;
+  double tauminn, dlntau;
+  const double* th;
+  const double* dotmu_pmin;
+  // time steps
+  int nt;
+  const double* ts;
+  // Galileon background
+  double c2, c3, c4, c5, cG, h0, orad;
+  int ngal;
+  double gal_lnq_inv, gal_a0;  // index guess: i ~ log(a/a0)*gal_lnq_inv
+  const double* gal;
+  // source k grid and output
+  int nk;
+  const double* k;
+  double* Src;    // [nt][S][nk]   (== Fortran Src(nk,S,nt))
+  double* ddSrc;  // same shape, second derivatives along k
+  // line-of-sight stage
+  GcRegions TimeSteps;
+  int nq;
+  const double* q;    // [nq]
+  const double* dq;   // [nq]
+  double* Delta;      // [nq][nl][S]  (== Fortran Delta_p_l_k(S,nl,nq))
+  // primordial power + C_l
+  double ScalarPowerAmp, an, n_run, n_runrun, k_0_scalar;
+  double* iCl;        // [ntype][nl]
+  double* Cl;         // [ntype][lmax-1]
+};

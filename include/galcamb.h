@@ -1,0 +1,130 @@
+/* galcamb.h -- C ABI of libgalcamb_b200.so: the B200 implementation of the scalar CMB transfer path of
+ * the Galileon fork of CAMB (ClementLeloup/cosmomc_galileon).
+ *
+ * Convention = the reference's own iso_c_binding convention (camb/interface.f90:7-92, camb/galileon.cc):
+ * trailing-underscore symbols, every scalar argument BY REFERENCE, arrays as plain pointers the caller owns
+ * (Fortran: type(C_PTR), value + C_LOC(array(1))), integer status return (0 = ok, otherwise a CAMB error id of
+ * camb/constants.f90:70-79), never exit().  All floating-point data are float64.  No CUDA / torch types appear.
+ *
+ * What each entry point replaces in the reference:
+ *   galcamb_evolve_sources_   the OpenMP loop over source k-modes            camb/cmbmain.f90:201-206
+ *                             (DoSourcek :662, CalcScalarSources :917, GaugeInterface_EvolveScal
+ *                              camb/equations_galileon.f90:314, dverk camb/subroutines.f90:370, derivs/output)
+ *   galcamb_los_integrate_    InitSourceInterpolation camb/cmbmain.f90:244 (:1267) and the OpenMP loop over
+ *                             integration k-modes :263-267 (SourceToTransfers :483, InterpolateSources :1355,
+ *                             DoFlatIntegration :1500)
+ *   galcamb_scalar_cls_       CalcScalCls camb/cmbmain.f90:2167 + InterpolateCls :2450
+ *   galcamb_set_bessels_      InitSpherBessels / GenerateBessels camb/bessels.f90:34-120
+ * Everything before (CAMBParams_Set, init_background, inithermo ...) and after (lensing, file output) stays in
+ * the Fortran host; the host hands over the tables it has after InitVars through galcamb_model.
+ *
+ * Threading: like CAMB itself (camb/cmbmain.f90:7-8) one context = one model batch at a time; call from one
+ * host thread per GPU.  Device buffers are owned by the library, host buffers by the caller.
+ */
+#ifndef GALCAMB_H
+#define GALCAMB_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GALCAMB_MAX_NU 3
+#define GALCAMB_MAX_NQ 5
+#define GALCAMB_MAX_REGIONS 16
+
+/* One region of a Ranges grid (camb/utils.F90:8-20). */
+typedef struct galcamb_region {
+  double Low, High, delta;
+  int start_index; /* 1-based index of the first point of the region, as in the reference */
+  int IsLog;
+} galcamb_region;
+
+/* The state the Fortran host holds after CAMBParams_Set + InitVars (camb/cmbmain.f90:722) for ONE model. */
+typedef struct galcamb_model {
+  /* camb/modules.f90:171-193 */
+  double grhom, grhog, grhor, grhob, grhoc, grhov, grhornomass, grhok;
+  double adotrad, tau0, taurst, taurend, tau_maxvis;
+  double tight_tau, matter_verydom_tau;          /* ThermoData, camb/modules.f90:2717-2718 */
+  double epsw;                                   /* GaugeInterface, camb/equations_galileon.f90:271 */
+  double max_etak_scalar;                        /* camb/cmbmain.f90:752-753 */
+  double AccuracyBoost, lAccuracyBoost;          /* camb/modules.f90:202-214 */
+  int use_galileon, DoLateRadTruncation, HighAccuracyDefault, AccuratePolarization, AccurateReionization;
+  int WantLateTime;                              /* camb/cmbmain.f90:137 ; selects 2 or 3 sources */
+  int MassiveNuMethod;                           /* camb/modules.f90:56 */
+  /* massive neutrinos: camb/modules.f90:186-189, :1570-1577 ; GaugeInterface :274 */
+  int Nu_mass_eigenstates, Num_Nu_massive, nqmax;
+  double grhormass[GALCAMB_MAX_NU], nu_masses[GALCAMB_MAX_NU];
+  double nu_q[GALCAMB_MAX_NQ], nu_int_kernel[GALCAMB_MAX_NQ];
+  double nu_tau_notmassless[GALCAMB_MAX_NQ][GALCAMB_MAX_NU]; /* [iq][eigenstate] */
+  double nu_tau_nonrelativistic[GALCAMB_MAX_NU], nu_tau_massive[GALCAMB_MAX_NU];
+  double dlnam;
+  const double *nu_r1, *nu_p1, *nu_dr1, *nu_dp1, *nu_ddr1, *nu_ddp1; /* [2000] each, camb/modules.f90:1562-1566 */
+  /* thermo tables on the log-tau grid, camb/modules.f90:2705-2714 */
+  int nthermo;
+  double tauminn, dlntau;
+  const double *cs2, *dcs2, *dotmu, *ddotmu, *dddotmu; /* [nthermo] each */
+  /* output time grid TimeSteps and the per-step visibility arrays, camb/modules.f90:2715, :3106-3146 */
+  int nt;
+  const double *tau, *dtau;                              /* TimeSteps%points, %dpoints */
+  const double *vis, *dvis, *ddvis, *expmmu, *opac, *dopac;
+  int n_tau_regions;
+  galcamb_region tau_regions[GALCAMB_MAX_REGIONS];       /* TimeSteps%R(1:count), for Ranges_IndexOf */
+  /* Galileon background owned by galileon.cc (camb/galileon.cc:72-92, :666-682) */
+  double c2, c3, c4, c5, cG, h0, orad;
+  int ngal;                                               /* 30001 points */
+  const double *gal_a, *gal_h, *gal_x;                    /* ascending a; h = hbar(a); x = dpi/da */
+  /* k grids */
+  int nk;
+  const double* k;                                        /* Evolve_q%points */
+  int nq;
+  const double *q, *dq;                                   /* ThisCT%q%points, %dpoints */
+  /* primordial power, camb/power_tilt.f90:60-92 */
+  double ScalarPowerAmp, an, n_run, n_runrun, k_0_scalar;
+  int lmax;                                               /* CP%Max_l */
+} galcamb_model;
+
+/* --- context --------------------------------------------------------------------------------------- */
+int galcamb_init_(const int* device);
+void galcamb_free_(void);
+const char* galcamb_last_error_(void);
+int galcamb_sizeof_model_(void); /* sizeof(galcamb_model) as compiled, for binding self-checks */
+int galcamb_get_bessels_(int* nx, double* xs, double* ajl, double* ajlpr); /* x grid and tables [nl][nx] (tests) */
+
+/* l samples (lSamp%l(1:l0)), Bessel x-range and accuracy: builds ajl/ajlpr on the device once and caches
+ * them across models like camb/bessels.f90:40-41. */
+int galcamb_set_bessels_(const int* ls, const int* nl, const int* kmaxfile, const double* AccuracyBoost);
+/* fiducial template highL_CL_template(lmin:lmax_tmpl, 1:3) = TT,EE,TE (camb/modules.f90:1222-1245), laid out
+ * [type][l-2]; pass lmax_tmpl = 0 for use_spline_template = F. */
+int galcamb_set_template_(const double* tmpl, const int* lmax_tmpl);
+
+/* --- batch of models ------------------------------------------------------------------------------- */
+int galcamb_batch_begin_(const int* nmodels);
+int galcamb_set_model_(const int* slot, const galcamb_model* m); /* slot = 0..nmodels-1; copies host -> device */
+
+/* stage 1+2: Src(nk, S, nt) for every slot */
+int galcamb_evolve_sources_(void);
+/* stage 3: ddSrc and Delta_p_l_k(S, nl, nq) for every slot */
+int galcamb_los_integrate_(void);
+/* stage 4: iCl_scalar(nl, ntype) and Cl_scalar(lmin:lmax, ntype) for every slot */
+int galcamb_scalar_cls_(void);
+
+/* results (device -> host); layouts are the Fortran ones, column-major:
+ *   Src(nk,S,nt)   Delta_p_l_k(S,nl,nq)   iCl(nl,ntype)   Cl(lmin:lmax, ntype), ntype = 3 (TT,EE,TE) or 6 */
+int galcamb_get_sources_(const int* slot, double* Src);
+int galcamb_put_sources_(const int* slot, const double* Src); /* feed stage 3 with host-computed sources */
+int galcamb_get_transfers_(const int* slot, double* Delta_p_l_k);
+int galcamb_get_cls_(const int* slot, double* iCl, double* Cl); /* either pointer may be NULL */
+int galcamb_get_status_(const int* slot, int* status);           /* per-slot CAMB error id */
+
+/* one call for a whole batch: set models, run stages 1-4, return Cl(lmin:lmax,3) per model contiguous */
+int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* Cl_out);
+
+/* measurement hooks (bench.py): last stage durations in ms (CUDA events on the library stream) and the
+ * algorithmic work counters of SURVEY.md section 8(d). */
+int galcamb_get_timings_(double* ms /*[8]: evolve, spline_k, los, cls, h2d, d2h, bessel, total*/);
+int galcamb_get_counters_(double* c /*[4]: n_derivs, sum_n, n_out, n_iter*/);
+int galcamb_sync_(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
