@@ -1,0 +1,56 @@
+"""Oracle vs fixtures: (i) the committed golden outputs (regression pin of the oracle itself), (ii) the only
+C_l data file the reference ships for this path, data/base_plikHM_TT_lowTEB.minimum.theory_cl (lensed LCDM;
+a ~1e-2 sanity pin at l<=400 where lensing is small; read only in the build container, skipped on the GPU box)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle_py import Oracle
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["config1", "config2"])
+def test_oracle_reproduces_golden(name):
+    z = np.load(os.path.join(GOLD, name + "_golden.npz"))
+    P = json.loads(bytes(z["params_json"]).decode())
+    o = Oracle(**P)
+    o.run()
+    np.testing.assert_allclose(o.Cl(), z["Cl"], rtol=1e-9)
+    np.testing.assert_allclose(o.iCl(), z["iCl"], rtol=1e-9)
+    S = o.Src()[::16]
+    assert np.max(np.abs(S - z["Src_t"])) / np.max(np.abs(z["Src_t"])) < 1e-10
+    D = o.Delta()[::32]
+    assert np.max(np.abs(D - z["Delta_q"])) / np.max(np.abs(z["Delta_q"])) < 1e-10
+    meta = json.loads(bytes(z["meta_json"]).decode())
+    assert o.get("n_derivs") == meta["n_derivs"] and o.get("n_iter") == meta["n_iter"]
+
+
+def test_grid_sizes_config2():
+    z = np.load(os.path.join(GOLD, "config2_golden.npz"))
+    ls = z["ls"]
+    # l sampling for lmax=2500, lSampleBoost=1, AccurateReionization (camb/modules.f90:876-1008)
+    expect = list(range(2, 11)) + list(range(11, 38, 2)) + list(range(40, 91, 5)) + [110, 130, 150, 175, 200] + list(range(250, 2501, 50))
+    assert list(ls) == expect and len(ls) == 85
+    assert 150 < len(z["k"]) < 260 and 2000 < len(z["q"]) < 3500 and 450 < len(z["tau"]) < 700
+
+
+REF_CL = "/root/reference/data/base_plikHM_TT_lowTEB.minimum.theory_cl"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CL), reason="reference tree not mounted")
+def test_lcdm_sanity_against_reference_theory_cl():
+    # best-fit point of data/base_plikHM_TT_lowTEB.minimum
+    o = Oracle(ombh2=0.02224017, omch2=0.1192851, omnuh2=0.000645, H0=67.44385, optical_depth=0.07602569,
+               ScalarPowerAmp=float(np.exp(3.081122) * 1e-10), an=0.9633217, YHe=0.245341, delta_redshift=0.5)
+    o.run()
+    cl = o.Cl() * (2.7255e6) ** 2
+    ref = np.loadtxt(REF_CL)
+    for l in (2, 5, 30, 60, 100, 150, 220, 300):
+        r = ref[ref[:, 0] == l][0]
+        assert abs(cl[0, l - 2] / r[1] - 1) < 8e-3, (l, cl[0, l - 2], r[1])
+    for l in (100, 150, 300):
+        r = ref[ref[:, 0] == l][0]
+        assert abs(cl[1, l - 2] / r[3] - 1) < 1.5e-2
