@@ -16,8 +16,9 @@ OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libgalcamb_b200.so")
 SOURCES = ["evolve.cu", "los.cu", "capi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17", "-Xcompiler",
-         "-fPIC", "-ccbin", "/usr/bin/g++"]
+FMAD = os.environ.get("GALCAMB_FMAD", "true")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=" + FMAD, "-std=c++17", "-Xcompiler",
+         "-fPIC", "-ccbin", "/usr/bin/g++"] + os.environ.get("GALCAMB_NVCC_EXTRA", "").split()
 
 
 def _stale(out, deps):

@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path():
-    return os.path.join(_HERE, "libgalcamb_b200.so")
+    # GALCAMB_LIB selects an alternative build of the same library (kernel experiments); default = in-tree build
+    return os.environ.get("GALCAMB_LIB") or os.path.join(_HERE, "libgalcamb_b200.so")
 
 
 class Region(C.Structure):

@@ -424,8 +424,10 @@ int galcamb_evolve_sources_(void) {
   CK(cudaSetDevice(g.device));
   if (int rc = upload_models()) return rc;
   const int nm = (int)g.slots.size();
-  // work items ordered by (k index descending, model): with >= 32 models a warp holds the same k index of 32
-  // cosmologies (lock-step control flow); expensive high-k items start first.
+  // work items ordered by (k index ascending, model): with >= 32 models a warp holds the same k index of 32
+  // cosmologies (lock-step control flow).  Low k first: those modes are integrated all the way to tau0
+  // (~7600 trial steps) while k*tau > max_etak_scalar stops the high-k modes at ~800 (camb/cmbmain.f90:1034),
+  // so the longest items start first and the short ones back-fill the SMs.
   int max_nk = 0, NV = 0;
   for (auto& s : g.slots) {
     max_nk = std::max(max_nk, s.host.nk);
@@ -444,7 +446,7 @@ int galcamb_evolve_sources_(void) {
     NV = std::max(NV, nv);
   }
   g.items.clear();
-  for (int kk = max_nk - 1; kk >= 0; kk--)
+  for (int kk = 0; kk < max_nk; kk++)
     for (int m = 0; m < nm; m++)
       if (kk < g.slots[m].host.nk) g.items.push_back(make_int2(m, kk));
   const int nitems = (int)g.items.size();

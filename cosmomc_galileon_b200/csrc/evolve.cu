@@ -14,6 +14,14 @@
 
 #include "evolve_device.cuh"
 
+// 4 warps per CTA, 3 CTAs per SM (168 registers): the warps of a CTA run derivs() in lock-step (see the main loop)
+#ifndef GC_EVOLVE_THREADS
+#define GC_EVOLVE_THREADS 128
+#endif
+#ifndef GC_EVOLVE_MINBLOCKS
+#define GC_EVOLVE_MINBLOCKS 3
+#endif
+
 namespace gc {
 
 enum Phase : int {
@@ -62,6 +70,58 @@ __constant__ double c_A[7][7] = {
     {2845924389000.0, -9754668000000.0, 7897110375000.0, -192082660000.0, 400298976000.0, 0, 201586000000.0}};
 __constant__ int c_Aused[7][7] = {{1, 0, 0, 0, 0, 0, 0}, {1, 1, 0, 0, 0, 0, 0}, {1, 1, 1, 0, 0, 0, 0}, {1, 1, 1, 1, 0, 0, 0},
                                   {1, 1, 1, 1, 1, 0, 0}, {1, 1, 1, 1, 1, 0, 0}, {1, 1, 1, 1, 1, 0, 1}};
+
+
+// w9 = y + temp * sum_j A[row][j] * w_(j+1), left to right as in camb/subroutines.f90:930-993
+template <int NC>
+__device__ __forceinline__ void stage_input_t(const double* __restrict__ y, double* __restrict__ w9, const double* const* kc,
+                                              const double* cf, int n, double temp) {
+  int i = 1;
+  for (; i + 3 <= n; i += 4) {
+    double yv[4], kv[NC][4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) yv[u] = AT(y, i + u);
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+      for (int u = 0; u < 4; u++) kv[c][u] = AT(kc[c], i + u);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      double acc = kv[0][u] * cf[0];
+#pragma unroll
+      for (int c = 1; c < NC; c++) acc = acc + kv[c][u] * cf[c];
+      AT(w9, i + u) = yv[u] + temp * acc;
+    }
+  }
+  for (; i <= n; i++) {
+    double acc = AT(kc[0], i) * cf[0];
+#pragma unroll
+    for (int c = 1; c < NC; c++) acc = acc + AT(kc[c], i) * cf[c];
+    AT(w9, i) = AT(y, i) + temp * acc;
+  }
+}
+
+__device__ __forceinline__ void stage_input(Lane& L, int row, int n, double temp) {
+  const double* y = col(L, 0);
+  double* w9 = col(L, 9);
+  const double* kc[6];
+  double cf[6];
+  int nc = 0;
+#pragma unroll
+  for (int jj = 0; jj < 7; jj++)
+    if (c_Aused[row][jj]) {
+      kc[nc] = col(L, jj + 1);
+      cf[nc] = c_A[row][jj];
+      nc++;
+    }
+  switch (nc) {
+    case 2: stage_input_t<2>(y, w9, kc, cf, n, temp); break;
+    case 3: stage_input_t<3>(y, w9, kc, cf, n, temp); break;
+    case 4: stage_input_t<4>(y, w9, kc, cf, n, temp); break;
+    case 5: stage_input_t<5>(y, w9, kc, cf, n, temp); break;
+    default: stage_input_t<6>(y, w9, kc, cf, n, temp); break;
+  }
+}
 
 struct Switches {
   double ktau, no_nu, no_phot, nu_massless, nu_nonrel, nu_massive, next;
@@ -325,15 +385,10 @@ __device__ __noinline__ void advance(Lane& L) {
         const double x = L.tau;
         const double temp = L.htrial / 1398169080000.0;
         if (s < 8) {
-          // input of stage s+1 : row s-1 of the tableau
-          const int row = s - 1;
-          for (int i = 1; i <= n; i++) {
-            double acc = AT(col(L, 1), i) * c_A[row][0];
-#pragma unroll
-            for (int jj = 1; jj < 7; jj++)
-              if (c_Aused[row][jj]) acc = acc + AT(col(L, jj + 1), i) * c_A[row][jj];
-            AT(w9, i) = AT(y, i) + temp * acc;
-          }
+          // input of stage s+1 : row s-1 of the tableau.  One specialised, 4-way batched loop per stage so that
+          // the (1 + #columns) x 4 independent loads of a batch are in flight together (the columns live in
+          // L2/HBM; a one-element-at-a-time loop stalls on every element).
+          stage_input(L, s - 1, n, temp);
           double frac;
           switch (s) {
             case 2: frac = 4.0 / 15.0; break;
@@ -358,14 +413,34 @@ __device__ __noinline__ void advance(Lane& L) {
         const double *w1 = col(L, 1), *w3 = col(L, 3), *w4 = col(L, 4), *w5 = col(L, 5), *w6 = col(L, 6), *w7 = col(L, 7),
                      *w8 = col(L, 8);
         double errn = 0.0;
-        for (int i = 1; i <= n; i++) {
-          AT(w9, i) = AT(y, i) + temp * (AT(w1, i) * 104862681000.0 + AT(w3, i) * 545186250000.0 + AT(w4, i) * 446637345000.0 +
-                                         AT(w5, i) * 188806464000.0 + AT(w7, i) * 15076875000.0 + AT(w8, i) * 97599465000.0);
-          const double w2 = (AT(w1, i) * 8738556750.0 + AT(w3, i) * 9735468750.0 - AT(w4, i) * 9709507500.0 +
-                             AT(w5, i) * 8582112000.0 + AT(w6, i) * 95329710000.0 - AT(w7, i) * 15076875000.0 -
-                             AT(w8, i) * 97599465000.0) /
-                            1398169080000.0;
-          errn = fmax(errn, fabs(w2) / fmax(1.0, fabs(AT(y, i))));
+        {
+          int i = 1;
+          for (; i + 1 <= n; i += 2) {  // 2-way batched: 2 x 8 independent loads in flight
+            double v[2][8];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+              v[u][0] = AT(y, i + u); v[u][1] = AT(w1, i + u); v[u][2] = AT(w3, i + u); v[u][3] = AT(w4, i + u);
+              v[u][4] = AT(w5, i + u); v[u][5] = AT(w6, i + u); v[u][6] = AT(w7, i + u); v[u][7] = AT(w8, i + u);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+              AT(w9, i + u) = v[u][0] + temp * (v[u][1] * 104862681000.0 + v[u][2] * 545186250000.0 + v[u][3] * 446637345000.0 +
+                                               v[u][4] * 188806464000.0 + v[u][6] * 15076875000.0 + v[u][7] * 97599465000.0);
+              const double w2 = (v[u][1] * 8738556750.0 + v[u][2] * 9735468750.0 - v[u][3] * 9709507500.0 + v[u][4] * 8582112000.0 +
+                                 v[u][5] * 95329710000.0 - v[u][6] * 15076875000.0 - v[u][7] * 97599465000.0) /
+                                1398169080000.0;
+              errn = fmax(errn, fabs(w2) / fmax(1.0, fabs(v[u][0])));
+            }
+          }
+          for (; i <= n; i++) {
+            AT(w9, i) = AT(y, i) + temp * (AT(w1, i) * 104862681000.0 + AT(w3, i) * 545186250000.0 + AT(w4, i) * 446637345000.0 +
+                                           AT(w5, i) * 188806464000.0 + AT(w7, i) * 15076875000.0 + AT(w8, i) * 97599465000.0);
+            const double w2 = (AT(w1, i) * 8738556750.0 + AT(w3, i) * 9735468750.0 - AT(w4, i) * 9709507500.0 +
+                               AT(w5, i) * 8582112000.0 + AT(w6, i) * 95329710000.0 - AT(w7, i) * 15076875000.0 -
+                               AT(w8, i) * 97599465000.0) /
+                              1398169080000.0;
+            errn = fmax(errn, fabs(w2) / fmax(1.0, fabs(AT(y, i))));
+          }
         }
         L.est = errn * L.hmag * 1.0;
         L.ind = 5;
@@ -417,7 +492,7 @@ __device__ __noinline__ void advance(Lane& L) {
 }
 
 // items[i] = (model index, k index); workspace = nwarps * GC_NCOL * NV * 32 doubles.
-__global__ void __launch_bounds__(128) evolve_sources_kernel(const DevModel* __restrict__ models, const int2* __restrict__ items,
+__global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve_sources_kernel(const DevModel* __restrict__ models, const int2* __restrict__ items,
                                                              int nitems, double* __restrict__ workspace, int NV,
                                                              int* __restrict__ status,
                                                              unsigned long long* __restrict__ counters) {
@@ -482,10 +557,17 @@ __global__ void __launch_bounds__(128) evolve_sources_kernel(const DevModel* __r
       L.phase = PH_NEXT_OUTPUT;
     }
   }
+  // All warps of the CTA run the RHS evaluation together: the kernel's hot loop is ~8k straight-line
+  // instructions (far beyond the 32 KB L1.5 instruction cache), so warps that reach derivs() at the same time
+  // share one instruction stream from L2 instead of fetching it once per warp.
   for (;;) {
     if (L.phase != PH_DONE) advance(L);
     const bool need = L.phase != PH_DONE;
+#if GC_EVOLVE_THREADS > 32
+    if (!__syncthreads_or(need)) break;
+#else
     if (!__any_sync(0xffffffffu, need)) break;
+#endif
     if (need) {
       derivs(*L.M, L.e, L.req_tau, col(L, L.req_in), col(L, L.req_out));
       L.n_derivs++;
@@ -514,7 +596,7 @@ extern "C" void gc_upload_constants() {
 
 extern "C" cudaError_t gc_launch_evolve(const DevModel* models, const int2* items, int nitems, double* workspace, int NV,
                                         int* status, unsigned long long* counters, cudaStream_t stream) {
-  const int threads = 128;
+  const int threads = GC_EVOLVE_THREADS;
   const int blocks = (nitems + threads - 1) / threads;
   gc::evolve_sources_kernel<<<blocks, threads, 0, stream>>>(models, items, nitems, workspace, NV, status, counters);
   return cudaGetLastError();
