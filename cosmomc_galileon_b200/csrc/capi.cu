@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -22,7 +24,7 @@ extern "C" cudaError_t gc_launch_bessels(double2*, const double*, const int*, do
 extern "C" cudaError_t gc_launch_spline_k(const DevModel*, int, int, cudaStream_t);
 extern "C" cudaError_t gc_launch_los(const DevModel*, int, int, int, int, const double2*, const double*, const int*, int, int,
                                      unsigned long long*, cudaStream_t);
-extern "C" cudaError_t gc_launch_zero(double*, size_t, cudaStream_t);
+extern "C" cudaError_t gc_launch_zero_delta(const DevModel*, int, int, cudaStream_t);
 extern "C" cudaError_t gc_launch_cls(const DevModel*, int, const int*, int, int, int, const double*, int, cudaStream_t);
 
 namespace {
@@ -35,7 +37,19 @@ struct Slot {
   double* d_out = nullptr;     // Src | ddSrc | Delta | iCl | Cl
   size_t out_cap = 0;
   int lmax = 0, ntype = 3, status = 0;
-  std::vector<double> staging;
+  double* staging = nullptr;  // pinned host buffer (packed AoS tables)
+  size_t staging_cap = 0;
+  size_t total = 0, n_th = 0, n_pm = 0, n_ts = 0, n_gal = 0;
+  int m_nk = 0, m_nq = 0, m_lmax = 0;
+  int ensure_staging(size_t n) {
+    if (n <= staging_cap) return 0;
+    if (staging) cudaFreeHost(staging);
+    staging = nullptr;
+    staging_cap = 0;
+    if (cudaMallocHost((void**)&staging, n * sizeof(double)) != cudaSuccess) return 1;
+    staging_cap = n;
+    return 0;
+  }
 };
 
 struct Ctx {
@@ -187,6 +201,7 @@ void galcamb_free_(void) {
   for (auto& s : g.slots) {
     if (s.d_tables) cudaFree(s.d_tables);
     if (s.d_out) cudaFree(s.d_out);
+    if (s.staging) cudaFreeHost(s.staging);
   }
   g.slots.clear();
   for (void* p : {(void*)g.d_ls, (void*)g.d_xs, (void*)g.d_bess, (void*)g.d_tmpl, (void*)g.d_nu_tab, (void*)g.d_models,
@@ -280,13 +295,13 @@ int galcamb_batch_begin_(const int* nmodels) {
   return 0;
 }
 
-int galcamb_set_model_(const int* slot, const galcamb_model* m) {
+static int pack_model(int islot, const galcamb_model* m) {
+  const int* slot = &islot;
   if (!g.ready) return fail(100, "not initialised");
   if (*slot < 0 || *slot >= (int)g.slots.size()) return fail(5, "bad slot");
   if (g.nl == 0) return fail(5, "galcamb_set_bessels_ must be called first");
   if (m->Nu_mass_eigenstates > GC_MAX_NU || m->nqmax > GC_MAX_NQ) return fail(5, "too many neutrino eigenstates / q nodes");
   if (m->n_tau_regions > GC_MAX_REGIONS) return fail(5, "too many TimeSteps regions");
-  CK(cudaSetDevice(g.device));
   Slot& s = g.slots[*slot];
   DevModel& D = s.host;
   D = DevModel{};
@@ -309,16 +324,6 @@ int galcamb_set_model_(const int* slot, const galcamb_model* m) {
   }
   for (int qn = 0; qn < GC_MAX_NQ; qn++) { D.nu_q[qn] = m->nu_q[qn]; D.nu_int_kernel[qn] = m->nu_int_kernel[qn]; }
   D.dlnam = m->dlnam;
-  if (m->Num_Nu_massive != 0 && !g.nu_tab_set) {
-    if (!m->nu_r1) return fail(5, "massive neutrinos without tables");
-    std::vector<double> t((size_t)GC_NRHOPN * 6);
-    for (int i = 0; i < GC_NRHOPN; i++) {
-      t[i * 6 + 0] = m->nu_r1[i]; t[i * 6 + 1] = m->nu_dr1[i]; t[i * 6 + 2] = m->nu_p1[i];
-      t[i * 6 + 3] = m->nu_dp1[i]; t[i * 6 + 4] = m->nu_ddr1[i]; t[i * 6 + 5] = m->nu_ddp1[i];
-    }
-    CK(cudaMemcpy(g.d_nu_tab, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
-    g.nu_tab_set = true;
-  }
   D.nu_tab = g.d_nu_tab;
   D.nthermo = m->nthermo; D.tauminn = m->tauminn; D.dlntau = m->dlntau;
   D.nt = m->nt; D.nk = m->nk; D.nq = m->nq;
@@ -340,9 +345,8 @@ int galcamb_set_model_(const int* slot, const galcamb_model* m) {
   D.ngal = ngal;
   const size_t n_th = (size_t)m->nthermo * 5, n_pm = m->nthermo, n_ts = (size_t)m->nt * 8, n_gal = (size_t)ngal * 5;
   const size_t total = n_th + n_pm + n_ts + n_gal + m->nk + 2 * (size_t)m->nq;
-  std::vector<double>& h = s.staging;
-  h.resize(total);
-  double* p = h.data();
+  if (s.ensure_staging(total)) return fail(100, "cudaMallocHost staging");
+  double* p = s.staging;
   for (int i = 0; i < m->nthermo; i++) {
     p[i * 5 + 0] = m->cs2[i]; p[i * 5 + 1] = m->dcs2[i]; p[i * 5 + 2] = m->dotmu[i];
     p[i * 5 + 3] = m->ddotmu[i]; p[i * 5 + 4] = m->dddotmu[i];
@@ -378,19 +382,37 @@ int galcamb_set_model_(const int* slot, const galcamb_model* m) {
   std::copy(m->k, m->k + m->nk, p); p += m->nk;
   std::copy(m->q, m->q + m->nq, p); p += m->nq;
   std::copy(m->dq, m->dq + m->nq, p); p += m->nq;
+  s.total = total; s.n_th = n_th; s.n_pm = n_pm; s.n_ts = n_ts; s.n_gal = n_gal; s.m_nk = m->nk; s.m_nq = m->nq; s.m_lmax = m->lmax;
+  return 0;
+}
+
+static int upload_model(int islot, const galcamb_model* m) {
+  Slot& s = g.slots[islot];
+  DevModel& D = s.host;
+  if (m && m->Num_Nu_massive != 0 && !g.nu_tab_set) {
+    if (!m->nu_r1) return fail(5, "massive neutrinos without tables");
+    std::vector<double> t((size_t)GC_NRHOPN * 6);
+    for (int i = 0; i < GC_NRHOPN; i++) {
+      t[i * 6 + 0] = m->nu_r1[i]; t[i * 6 + 1] = m->nu_dr1[i]; t[i * 6 + 2] = m->nu_p1[i];
+      t[i * 6 + 3] = m->nu_dp1[i]; t[i * 6 + 4] = m->nu_ddr1[i]; t[i * 6 + 5] = m->nu_ddp1[i];
+    }
+    CK(cudaMemcpy(g.d_nu_tab, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    g.nu_tab_set = true;
+  }
+  const size_t total = s.total, n_th = s.n_th, n_pm = s.n_pm, n_ts = s.n_ts, n_gal = s.n_gal;
   if (grow(&s.d_tables, &s.tables_cap, total)) return fail(100, "cudaMalloc tables");
-  CK(cudaMemcpyAsync(s.d_tables, h.data(), total * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(s.d_tables, s.staging, total * sizeof(double), cudaMemcpyHostToDevice, g.stream));
   double* d = s.d_tables;
   D.th = d; d += n_th;
   D.dotmu_pmin = d; d += n_pm;
   D.ts = d; d += n_ts;
   D.gal = d; d += n_gal;
-  D.k = d; d += m->nk;
-  D.q = d; d += m->nq;
-  D.dq = d; d += m->nq;
+  D.k = d; d += s.m_nk;
+  D.q = d; d += s.m_nq;
+  D.dq = d; d += s.m_nq;
   // ---- outputs
-  const size_t n_src = (size_t)m->nk * D.SourceNum * m->nt, n_delta = (size_t)D.SourceNum * g.nl * m->nq;
-  const size_t n_icl = (size_t)s.ntype * g.nl, n_cl = (size_t)s.ntype * (m->lmax - 1);
+  const size_t n_src = (size_t)s.m_nk * D.SourceNum * m->nt, n_delta = (size_t)D.SourceNum * g.nl * s.m_nq;
+  const size_t n_icl = (size_t)s.ntype * g.nl, n_cl = (size_t)s.ntype * (s.m_lmax - 1);
   if (grow(&s.d_out, &s.out_cap, 2 * n_src + n_delta + n_icl + n_cl)) return fail(100, "cudaMalloc outputs");
   d = s.d_out;
   D.Src = d; d += n_src;
@@ -401,6 +423,14 @@ int galcamb_set_model_(const int* slot, const galcamb_model* m) {
   s.set = true;
   s.status = 0;
   return 0;
+}
+
+int galcamb_set_model_(const int* slot, const galcamb_model* m) {
+  if (!g.ready) return fail(100, "not initialised");
+  if (*slot < 0 || *slot >= (int)g.slots.size()) return fail(5, "bad slot");
+  CK(cudaSetDevice(g.device));
+  if (int rc = pack_model(*slot, m)) return rc;
+  return upload_model(*slot, m);
 }
 
 static int upload_models() {
@@ -432,17 +462,21 @@ int galcamb_evolve_sources_(void) {
   for (auto& s : g.slots) {
     max_nk = std::max(max_nk, s.host.nk);
     const DevModel& D = s.host;
+    // upper bound of nvar over k, from the two branches of GetNumEqns (camb/equations_galileon.f90:854-870)
     const double lAB = D.lAccuracyBoost;
-    int lmaxg = std::max((int)std::lround(11 * lAB), 3);
-    if (D.AccurateReionization) lmaxg = std::max(lmaxg, 4 * std::max(3, (int)std::lround(8 * lAB)));
-    int lmaxgpol = std::max(lmaxg, 2 * std::max(3, (int)std::lround(8 * lAB)));
-    lmaxgpol = std::min(lmaxgpol, std::max((int)std::lround(11 * lAB), 2 * std::max(3, (int)std::lround(8 * lAB))));
     double mx = 0;
     for (int i = 0; i < D.n_eig; i++) mx = std::max(mx, D.nu_masses[i]);
-    const int lmaxnr = std::max((int)std::lround((mx > 700 ? 32 : 14) * lAB), 3);
     const int lmaxnu = D.Num_Nu_massive ? std::max(3, (int)std::lround((mx > 700 ? 15 : 10) * lAB)) : 0;
-    int nv = 5 + (lmaxg + 1) + (lmaxnr + 1) + lmaxgpol - 1 + 2;
-    if (D.Num_Nu_massive) nv += (lmaxnu + 1) + D.n_eig * D.nqmax * (lmaxnu + 1);
+    const int nu_eqs = D.Num_Nu_massive ? (lmaxnu + 1) + D.n_eig * D.nqmax * (lmaxnu + 1) : 0;
+    // q >= 0.05
+    int gB = std::max((int)std::lround(((D.HighAccuracyDefault && D.AccuratePolarization) ? 11 : 8) * lAB), 3);
+    int pB = D.AccuratePolarization ? gB : std::max((int)std::lround(4 * lAB), 3);
+    int rB = std::max((int)std::lround(((mx > 700 && D.HighAccuracyDefault) ? 32 : 14) * lAB), 3);
+    // q < 0.05
+    int gA = std::max(3, (int)std::lround(8 * lAB)), pA = gA, rA = std::max(3, (int)std::lround(7 * lAB));
+    if (D.AccurateReionization) { gA *= 4; pA *= 2; }
+    const int nvA = 5 + (gA + 1) + (rA + 1) + pA - 1 + 2 + nu_eqs, nvB = 5 + (gB + 1) + (rB + 1) + pB - 1 + 2 + nu_eqs;
+    const int nv = std::max(nvA, nvB);
     NV = std::max(NV, nv);
   }
   g.items.clear();
@@ -504,7 +538,7 @@ int galcamb_los_integrate_(void) {
   CK(cudaEventRecord(g.ev[2], g.stream));
   CK(gc_launch_spline_k(g.d_models, nm, max_rows, g.stream));
   CK(cudaEventRecord(g.ev[3], g.stream));
-  for (auto& s : g.slots) CK(gc_launch_zero(s.host.Delta, (size_t)s.host.SourceNum * g.nl * s.host.nq, g.stream));
+  CK(gc_launch_zero_delta(g.d_models, nm, g.nl, g.stream));
   CK(cudaMemsetAsync(g.d_counters + 3, 0, sizeof(unsigned long long), g.stream));
   CK(gc_launch_los(g.d_models, nm, max_nq, max_nt, S, g.d_bess, g.d_xs, g.d_ls, g.nx, g.nl, g.d_counters + 3, g.stream));
   CK(cudaEventRecord(g.ev[4], g.stream));
@@ -582,8 +616,28 @@ int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* 
   if (!g.ready) return fail(100, "not initialised");
   int rc = galcamb_batch_begin_(nmodels);
   if (rc) return rc;
-  for (int i = 0; i < *nmodels; i++)
-    if ((rc = galcamb_set_model_(&i, &models[i]))) return rc;
+  CK(cudaSetDevice(g.device));
+  {  // pack the AoS tables (+ background spline) of all models on the host cores, then upload slot by slot
+    const int n = *nmodels;
+    const int nth = std::max(1, std::min<int>(n, (int)std::thread::hardware_concurrency()));
+    std::vector<int> rcs(nth, 0);
+    std::vector<std::thread> pool;
+    std::atomic<int> next(0);
+    for (int t = 0; t < nth; t++)
+      pool.emplace_back([&, t]() {
+        cudaSetDevice(g.device);  // pinned-buffer growth inside pack_model
+        for (;;) {
+          const int i = next.fetch_add(1);
+          if (i >= n) break;
+          if (int r = pack_model(i, &models[i])) rcs[t] = r;
+        }
+      });
+    for (auto& th : pool) th.join();
+    for (int r : rcs)
+      if (r) return r;
+    for (int i = 0; i < n; i++)
+      if ((rc = upload_model(i, &models[i]))) return rc;
+  }
   if ((rc = galcamb_evolve_sources_())) return rc;
   if ((rc = galcamb_los_integrate_())) return rc;
   if ((rc = galcamb_scalar_cls_())) return rc;

@@ -14,7 +14,7 @@
 
 #include "evolve_device.cuh"
 
-// 4 warps per CTA, 3 CTAs per SM (168 registers): the warps of a CTA run derivs() in lock-step (see the main loop)
+// 4 warps per CTA, 3 CTAs per SM (168 registers); the warps of a CTA run derivs() in lock-step (see the main loop)
 #ifndef GC_EVOLVE_THREADS
 #define GC_EVOLVE_THREADS 128
 #endif
@@ -40,7 +40,8 @@ enum Phase : int {
 struct Lane {
   EV e;
   const DevModel* M;
-  double* ws;  // lane base of the warp workspace
+  double* ws;  // lane base of the warp's global workspace: columns 1..8 (the eight stage derivatives)
+  double* sm;  // lane base of the warp's shared-memory block: column 0 (y) and column 9 (stage input)
   int NV;
   int kidx;
   int phase, stage, j, ind, after_switch;
@@ -56,7 +57,15 @@ struct Lane {
   unsigned long long n_derivs, sum_n, n_out;
 };
 
-__device__ __forceinline__ double* col(const Lane& L, int c) { return L.ws + (size_t)c * L.NV * GC_LANES; }
+// Column placement.  Default: all ten columns in the warp-interleaved global workspace (12 warps/SM resident).
+// Optional (GALCAMB_EVOLVE_SMEM=1): y (0) and the stage input w9 (9) -- what derivs() reads with latency-critical
+// loads -- in shared memory, the stage derivatives in global memory.  Measured on B200 (profiles/README.md): the
+// shared-memory placement is 1.3x faster per warp but only 4 warps/SM fit, so the global placement wins at
+// every batch size; it stays as a switch for the follow-up work on splitting the state between the two.
+__device__ __forceinline__ double* col(const Lane& L, int c) {
+  if (L.sm && c == 9) return L.sm;
+  return L.ws + (size_t)c * L.NV * GC_LANES;
+}
 
 // Verner 6(5) stage tableau of camb/subroutines.f90:930-993: w9 = y + temp*(sum_j A[s][j]*w_j), evaluated left to
 // right with the reference's signs so that every partial sum is bit-identical to the Fortran expression.
@@ -479,7 +488,7 @@ __device__ __noinline__ void advance(Lane& L) {
       }
       case PH_OUT_DONE: {
         double src[3] = {0, 0, 0};
-        output_sources(M, e, col(L, 0), col(L, 2), M.ts + (size_t)(L.j - 1) * 8, L.tau, src);
+        output_sources(L.M, &L.e, col(L, 0), col(L, 2), M.ts + (size_t)(L.j - 1) * 8, L.tau, src);
         for (int s = 0; s < S; s++) M.Src[((size_t)(L.j - 1) * S + s) * M.nk + L.kidx] = src[s];
         L.n_out++;
         L.phase = PH_NEXT_OUTPUT;
@@ -495,7 +504,8 @@ __device__ __noinline__ void advance(Lane& L) {
 __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve_sources_kernel(const DevModel* __restrict__ models, const int2* __restrict__ items,
                                                              int nitems, double* __restrict__ workspace, int NV,
                                                              int* __restrict__ status,
-                                                             unsigned long long* __restrict__ counters) {
+                                                             unsigned long long* __restrict__ counters, int use_smem) {
+  extern __shared__ double gc_smem[];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int gwarp = tid >> 5;
@@ -511,6 +521,7 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
     L.kidx = it.y;
     L.NV = NV;
     L.ws = workspace + (size_t)gwarp * GC_NCOL * NV * GC_LANES + lane;
+    L.sm = use_smem ? gc_smem + (size_t)(threadIdx.x >> 5) * NV * GC_LANES + lane : nullptr;
     // DoSourcek, camb/cmbmain.f90:662-689
     L.e.q = M.k[it.y];
     L.e.pig = 0;
@@ -569,7 +580,7 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
     if (!__any_sync(0xffffffffu, need)) break;
 #endif
     if (need) {
-      derivs(*L.M, L.e, L.req_tau, col(L, L.req_in), col(L, L.req_out));
+      derivs(L.M, &L.e, L.req_tau, col(L, L.req_in), col(L, L.req_out));
       L.n_derivs++;
       L.sum_n += L.e.neq;
     }
@@ -596,8 +607,26 @@ extern "C" void gc_upload_constants() {
 
 extern "C" cudaError_t gc_launch_evolve(const DevModel* models, const int2* items, int nitems, double* workspace, int NV,
                                         int* status, unsigned long long* counters, cudaStream_t stream) {
-  const int threads = GC_EVOLVE_THREADS;
+  static int use_smem = -1;
+  if (use_smem < 0) {
+    const char* e = getenv("GALCAMB_EVOLVE_SMEM");
+    use_smem = (e && atoi(e)) ? 1 : 0;
+  }
+  int warps = GC_EVOLVE_THREADS / 32;
+  size_t smem = 0;
+  if (use_smem) {  // 2 columns x NV x 32 lanes x 8 B per warp; as many warps per CTA as fit in 227 KB
+    const size_t per_warp = (size_t)NV * GC_LANES * sizeof(double);
+    while (warps > 1 && warps * per_warp > 227 * 1024) warps--;
+    smem = warps * per_warp;
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(gc::evolve_sources_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = smem;
+    }
+  }
+  const int threads = 32 * warps;
   const int blocks = (nitems + threads - 1) / threads;
-  gc::evolve_sources_kernel<<<blocks, threads, 0, stream>>>(models, items, nitems, workspace, NV, status, counters);
+  gc::evolve_sources_kernel<<<blocks, threads, smem, stream>>>(models, items, nitems, workspace, NV, status, counters, use_smem);
   return cudaGetLastError();
 }

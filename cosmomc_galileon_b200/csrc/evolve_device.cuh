@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdint>
 
+#include "galileon_fast.cuh"
 #include "model.h"
 
 #define GC_LANES 32
@@ -778,8 +779,12 @@ __device__ inline void Nu_Intvsq(const DevModel& M, const EV& e, const double* y
 // ---------------------------------------------------------------- derivs
 // camb/equations_galileon.f90:2098-2589.  ay / ayp are workspace columns.  Writes e.pig / e.pigdot during
 // tight coupling exactly as the reference does (its value at a switch is the one left by the LAST call).
-__device__ __noinline__ void derivs(const DevModel& M, EV& e, double tau, const double* __restrict__ ay,
-                                    double* __restrict__ ayp) {
+__device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restrict__ ep, double tau,
+                                    const double* __restrict__ ay, double* __restrict__ ayp) {
+  // __restrict__ on every pointer: the state-vector stores below must not force reloads of the model constants
+  // (global) or of the lane's layout descriptor (local) after each store.
+  const DevModel& M = *Mp;
+  EV& e = *ep;
   const bool gal = M.use_galileon != 0;
   const double k = e.k, k2 = e.k2;
   const double a = AT(ay, 1), a2 = a * a;
@@ -793,12 +798,15 @@ __device__ __noinline__ void derivs(const DevModel& M, EV& e, double tau, const 
   // massive-neutrino background at this a (shared by MassiveNuVars, GetdHdX and dtauda)
   double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
   for (int i = 0; i < M.n_eig; i++) Nu_background(M, a * M.nu_masses[i], rhonu[i], pnu[i]);
-  double grhov_t = 0, xgal = 0, hub = 0, dh = 0, dx = 0, grhogal_t = 0, hbar = 0;
+  double grhov_t = 0, xgal = 0, grhogal_t = 0, hbar = 0;
+  GalFast F;
+  const GalConst GC{M.c2, M.c3, M.c4, M.c5, M.cG, M.h0, M.orad};
   if (gal) {
     gal_HX(M, a, hbar, xgal);
-    hub = a * hbar;
-    gal_GetdHdX(M, a, hub, xgal, pnu, dh, dx);
-    grhogal_t = gal_grhogal(M, a, hub, xgal);
+    double lam_nu = 0;
+    for (int i = 0; i < M.n_eig; i++) lam_nu += M.grhormass[i] * pnu[i];
+    gal_fast_background(GC, a, hbar, xgal, lam_nu, k, F);
+    grhogal_t = F.grhogal;
   } else {
     grhov_t = M.grhov * a2;
   }
@@ -807,7 +815,7 @@ __device__ __noinline__ void derivs(const DevModel& M, EV& e, double tau, const 
   double gpres = 0;
   gpres = gpres + (grhog_t + grhor_t) / 3;
   if (gal)
-    gpres = gpres + gal_gpresgal(M, a, hub, xgal, dh, dx);
+    gpres = gpres + F.gpresgal;
   else
     gpres = gpres + grhov_t * (-1.0);
   double grho_matter = grhob_t + grhoc_t;
@@ -852,7 +860,7 @@ __device__ __noinline__ void derivs(const DevModel& M, EV& e, double tau, const 
   double z = 0, dz, clxr, qr, pir, clxg, qg, pig = 0, dgrhogal_t;
   if (e.no_nu) {
     if (gal) {
-      dgrhogal_t = gal_Chigal(M, a, hub, xgal, dgrho, etak, dphi, dphiprime, k);
+      dgrhogal_t = gal_fast_Chigal(F, dgrho, etak, dphi, dphiprime);
       z = (0.5 * (dgrho + dgrhogal_t) / k + etak) / adotoa;
       dz = -adotoa * z - 0.5 * (dgrho + dgrhogal_t) / k;
     } else {
@@ -870,7 +878,7 @@ __device__ __noinline__ void derivs(const DevModel& M, EV& e, double tau, const 
   if (e.no_phot) {
     if (!e.no_nu) {
       if (gal) {
-        dgrhogal_t = gal_Chigal(M, a, hub, xgal, dgrho, etak, dphi, dphiprime, k);
+        dgrhogal_t = gal_fast_Chigal(F, dgrho, etak, dphi, dphiprime);
         z = (0.5 * (dgrho + dgrhogal_t) / k + etak) / adotoa;
         dz = -adotoa * z - 0.5 * (dgrho + dgrhogal_t) / k;
       } else {
@@ -895,9 +903,9 @@ __device__ __noinline__ void derivs(const DevModel& M, EV& e, double tau, const 
   const double pb43 = 4.0 / 3 * photbar;
   AT(ayp, 1) = adotoa * a;
   if (gal) {
-    dgrhogal_t = gal_Chigal(M, a, hub, xgal, dgrho, etak, dphi, dphiprime, k);
+    dgrhogal_t = gal_fast_Chigal(F, dgrho, etak, dphi, dphiprime);
     dgrho = dgrho + dgrhogal_t;
-    dgq = dgq + gal_qgal(M, a, hub, xgal, dgq, etak, dphi, dphiprime, k);
+    dgq = dgq + gal_fast_qgal(F, dgq, dphi, dphiprime);
   }
   z = (0.5 * dgrho / k + etak) / adotoa;
   const double sigma = (z + 1.5 * dgq / k2);
@@ -914,7 +922,7 @@ __device__ __noinline__ void derivs(const DevModel& M, EV& e, double tau, const 
     const double slip = -(2 * adotoa / (1 + pb43) + dopacity / opacity) * (vb - 3.0 / 4 * qg) +
                         (-adotdota * vb - k / 2 * adotoa * clxg + k * (cs2 * clxbdot - clxgdot / 4)) / (opacity * (1 + pb43));
     double dgs = grhog_t * pig + grhor_t * pir;
-    if (gal) dgs = dgs + gal_Pigal(M, a, hub, xgal, dh, dx, dgrho, dgq, dgs, etak, dphi, k);
+    if (gal) dgs = dgs + gal_fast_Pigal(GC, F, dgrho, dgq, dgs, etak, dphi);
     const double sigmadot = -2 * adotoa * sigma - dgs / k + etak;
     qgdot = k * (clxg / 4.0 - pig / 2.0) + opacity * slip;
     const double op2 = opacity * opacity;
@@ -993,7 +1001,7 @@ __device__ __noinline__ void derivs(const DevModel& M, EV& e, double tau, const 
     const double dotdeltaf = grhob_t * (clxbdot - 3 * adotoa * clxb) + grhoc_t * (clxcdot - 3 * adotoa * clxc) +
                              grhor_t * (clxrdot - 4 * adotoa * clxr) + grhog_t * (clxgdot - 4 * adotoa * clxg);
     AT(ayp, e.w_ix) = dphiprime;
-    AT(ayp, e.w_ix + 1) = gal_dphisecond(M, a, hub, xgal, dh, dx, dgrho, dgq, etak, dphi, dphiprime, k, dotdeltaf);
+    AT(ayp, e.w_ix + 1) = gal_fast_dphisecond(GC, F, dgrho, dgq, etak, dphi, dphiprime, dotdeltaf);
   }
   if (M.Num_Nu_massive == 0) return;
   for (int nu_i = 0; nu_i < M.n_eig; nu_i++) {
@@ -1050,9 +1058,11 @@ __device__ __noinline__ void derivs(const DevModel& M, EV& e, double tau, const 
 // ---------------------------------------------------------------- output
 // camb/equations_galileon.f90:1256-1576, everything after the derivs call at :1297.
 // ts = this output time's row {tau, dtau, vis, dvis, ddvis, expmmu, opac, dopac}.
-__device__ __noinline__ void output_sources(const DevModel& M, const EV& e, const double* __restrict__ y,
-                                            const double* __restrict__ yprime, const double* __restrict__ ts,
-                                            double tau, double* sources) {
+__device__ __noinline__ void output_sources(const DevModel* __restrict__ Mp, const EV* __restrict__ ep,
+                                            const double* __restrict__ y, const double* __restrict__ yprime,
+                                            const double* __restrict__ ts, double tau, double* __restrict__ sources) {
+  const DevModel& M = *Mp;
+  const EV& e = *ep;
   const bool gal = M.use_galileon != 0;
   const double vis = ts[2], dvis = ts[3], ddvis = ts[4], expmmu = ts[5], opac = ts[6], dopac = ts[7];
   double pol2 = 0, pol3 = 0, polprime2 = 0, polprime3 = 0;

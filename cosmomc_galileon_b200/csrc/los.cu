@@ -344,8 +344,10 @@ __global__ void __launch_bounds__(256) los_kernel(const DevModel* __restrict__ m
 }
 
 // zero Delta (l > llmax entries are never touched by los_kernel; reference: Init_ClTransfer camb/modules.f90:1175)
-__global__ void zero_kernel(double* p, size_t n) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0;
+__global__ void zero_delta_kernel(const DevModel* __restrict__ models, int nl) {
+  const DevModel& M = models[blockIdx.y];
+  const size_t n = (size_t)M.SourceNum * nl * M.nq;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) M.Delta[i] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ K4
@@ -490,8 +492,9 @@ extern "C" cudaError_t gc_launch_los(const DevModel* models, int nmodels, int ma
   return cudaGetLastError();
 }
 
-extern "C" cudaError_t gc_launch_zero(double* p, size_t n, cudaStream_t st) {
-  gc::zero_kernel<<<592, 256, 0, st>>>(p, n);
+extern "C" cudaError_t gc_launch_zero_delta(const DevModel* models, int nmodels, int nl, cudaStream_t st) {
+  dim3 g(64, nmodels);
+  gc::zero_delta_kernel<<<g, 256, 0, st>>>(models, nl);
   return cudaGetLastError();
 }
 

@@ -123,6 +123,9 @@ int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* 
 int galcamb_get_timings_(double* ms /*[8]: evolve, spline_k, los, cls, h2d, d2h, bessel, total*/);
 int galcamb_get_counters_(double* c /*[4]: n_derivs, sum_n, n_out, n_iter*/);
 int galcamb_sync_(void);
+/* FP64 FMA micro-benchmark (roofline denominator): out[0] = device peak TFLOP/s, out[1], out[2] = one warp per SM with
+ * 1 and 4 dependent chains (latency probes) */
+int galcamb_fp64_peak_(double* out);
 
 #ifdef __cplusplus
 }
