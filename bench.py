@@ -15,6 +15,7 @@ copy of the tables in HBM and its own ODE state, so no work is shared between re
 reference cannot be built in this image) on the host cores.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -142,7 +143,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("GALCAMB_BENCH_BATCH", "256")), help="parameter points per GPU per step")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("GALCAMB_BENCH_BATCH", "1024")), help="parameter points per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -237,7 +238,9 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        fp64_peak = float(os.environ.get("GALCAMB_FP64_PEAK_TFLOPS", "37.2"))
+        pk = np.zeros(3)
+        g.L.galcamb_fp64_peak_(ctypes.c_void_p(pk.ctypes.data))  # FP64 FMA micro-benchmark on this GPU, now
+        fp64_peak = float(pk[0]) if pk[0] > 0 else 37.2
         t_los = ev["los"] / args.steps * 1e-3
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -245,15 +248,15 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: Galileon scalar C_l lmax=2500 (camb/params.ini accuracy), batch of "
                                    "%d parameter points per GPU (replicas of tests/golden/config2_tables.npz)" % B,
-                       "batch_per_gpu": B, "l2_note": "per-step working set %.0f MB of ODE workspace + tables exceeds the 126 MB L2"
-                       % (B * 197 * 9.1e-3), "parallelism": "parameter points sharded across ranks; NCCL all-gather of C_l"},
+                       "batch_per_gpu": B, "l2_note": "inputs larger than L2: per-step working set = %.0f MB of model tables + %.0f MB of ODE "
+                       "workspace vs 126 MB L2" % (B * fixture.nbytes() / 1e6, B * 197 * 9.1e-3), "parallelism": "parameter points sharded across ranks; NCCL all-gather of C_l"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * fixture.nbytes()),
                     "d2h_bytes_per_step": int(out.nbytes)},
-            "gpu_launches": int(args.steps * (5 + B)),
+            "gpu_launches": int(args.steps * 6),  # evolve, spline_k, zero_delta, los, cl, cl_interp per step
             "clocks": clocks,
             "roofline": {"kernel": "evolve_sources_kernel", "bound": "fp64", "achieved": flop / t_ev / 1e12, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": flop / t_ev / 1e12 / fp64_peak,
-                         "peak_source": "nominal 148 SM x 64 FP64 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no FP64 figure)",
+                         "peak_source": "measured: galcamb_fp64_peak_ DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure; nominal 37.2)",
                          "traffic": None, "share_of_step": ev["evolve"] / (ev["evolve"] + ev["spline_k"] + ev["los"] + ev["cls"]),
                          "flop_per_spectrum": meta["flop_ode"], "ms_per_launch": 1e3 * t_ev},
             "roofline_los": {"kernel": "los_kernel", "bound": "hbm", "achieved": meta["bytes_los_operand"] * B / t_los / 1e9,
