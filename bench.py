@@ -173,7 +173,6 @@ def main():
         m.cstruct()
     lmax = fixture.d["lmax"]
     out = np.zeros((B, 3, lmax - 1))
-    gathered = torch.empty((world, B, 3, lmax - 1), dtype=torch.float64, device="cuda") if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -184,8 +183,8 @@ def main():
     def exchange(cl_host):
         # the path's one exchange step (parameter-batch mode): all-gather of the final C_l
         if world > 1:
-            mine = torch.from_numpy(cl_host).cuda(non_blocking=True)
-            dist.all_gather_into_tensor(gathered.view(world * B, 3, lmax - 1), mine)
+            from cosmomc_galileon_b200.sharding import gather_cls
+            return gather_cls(cl_host, world * B, device=torch.device("cuda", local))
 
     def step_resident():
         g.CalcScalarSources()

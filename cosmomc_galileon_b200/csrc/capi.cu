@@ -480,9 +480,21 @@ int galcamb_evolve_sources_(void) {
     NV = std::max(NV, nv);
   }
   g.items.clear();
-  for (int kk = 0; kk < max_nk; kk++)
-    for (int m = 0; m < nm; m++)
-      if (kk < g.slots[m].host.nk) g.items.push_back(make_int2(m, kk));
+  static int order = -1;
+  if (order < 0) {
+    const char* e = getenv("GALCAMB_ITEM_ORDER");  // 0: (k, model) lanes = cosmologies at one k ; 1: (model, k) lanes = adjacent k
+    order = e ? atoi(e) : 0;
+  }
+  if (order == 0) {
+    for (int kk = 0; kk < max_nk; kk++)
+      for (int m = 0; m < nm; m++)
+        if (kk < g.slots[m].host.nk) g.items.push_back(make_int2(m, kk));
+  } else {
+    // warps of 32 adjacent k of ONE model (constants warp-uniform), dealt low-k-first across models
+    for (int k0 = 0; k0 < max_nk; k0 += 32)
+      for (int m = 0; m < nm; m++)
+        for (int kk = k0; kk < std::min(k0 + 32, g.slots[m].host.nk); kk++) g.items.push_back(make_int2(m, kk));
+  }
   const int nitems = (int)g.items.size();
   if ((size_t)nitems > g.items_cap) {
     if (g.d_items) cudaFree(g.d_items);

@@ -59,6 +59,33 @@ def test_full_path_against_oracle(gpu, P):
     assert gpu.counters()["n_iter"] == o.get("n_iter")
 
 
+@pytest.mark.parametrize("kw,lmax", [(dict(DoLensing=1, AccuracyBoost=2), 3000), (dict(DoLensing=1, DoLateRadTruncation=0), 2650)],
+                         ids=["lensing_accuracyboost2", "cosmomc_settings"])
+def test_three_source_variants_against_oracle(gpu, kw, lmax):
+    """BASELINE configs[2] / configs[4] flavours: lensing source (S=3, six C_l types, Limber substitution in the LOS
+    stage), AccuracyBoost=2 (nqmax=4, halved steps, tol1=1e-4/e) and the CosmoMC setting DoLateRadTruncation=F
+    (SURVEY.md section 3.2).  lmax reduced to keep the single-model run short."""
+    from oracle_py import Oracle
+    from tables_from_oracle import tables_from_oracle
+    P = dict(GAL)
+    P.update(kw)
+    o = Oracle(lmax=lmax, **P)
+    o.run()
+    t = tables_from_oracle(o, P, lmax=lmax)
+    run_gpu(gpu, t)
+    S, So = gpu.Src(), o.Src()
+    assert S.shape[1] == 3
+    for s in range(3):
+        assert relmax(S[:, s], So[:, s]) < TOL_TRANSFER
+    assert relmax(gpu.Delta_p_l_k(), o.Delta()) < TOL_TRANSFER
+    icl, cl = gpu.Cls()
+    assert icl.shape[0] == 6
+    assert np.max(np.abs(icl[:3] / o.iCl()[:3] - 1)) < TOL_CL
+    assert np.max(np.abs(cl[:4] / o.Cl()[:4] - 1)) < TOL_CL  # TT, EE, TE, phi-phi
+    for t_ in (4, 5):  # phi-T and phi-E cross spectra change sign: compare on the max-norm
+        assert relmax(cl[t_], o.Cl()[t_]) < TOL_CL
+
+
 def test_bessel_tables_against_oracle(gpu):
     from oracle_py import Oracle
     o = Oracle(**LCDM)
