@@ -10,6 +10,7 @@
 // call of derivs() for all of its lanes.  Lanes of a warp therefore share the ~2 kFLOP RHS instruction stream
 // even when they sit in different Runge-Kutta stages, at different step sizes or in different output intervals;
 // only the short bookkeeping between evaluations diverges.
+#include <cstddef>
 #include <cstdio>
 
 #include "evolve_device.cuh"
@@ -19,7 +20,7 @@
 #define GC_EVOLVE_THREADS 128
 #endif
 #ifndef GC_EVOLVE_MINBLOCKS
-#define GC_EVOLVE_MINBLOCKS 3
+#define GC_EVOLVE_MINBLOCKS 2
 #endif
 
 namespace gc {
@@ -37,11 +38,16 @@ enum Phase : int {
   PH_DONE
 };
 
+#ifndef GC_HOT_IN_SMEM
+#define GC_HOT_IN_SMEM 1
+#endif
+#define GC_HOT_BYTES (offsetof(DevModel, adotrad))
+static_assert(GC_HOT_BYTES % 8 == 0, "hot block must be a whole number of doubles");
+
 struct Lane {
   EV e;
   const DevModel* M;
-  double* ws;  // lane base of the warp's global workspace: columns 1..8 (the eight stage derivatives)
-  double* sm;  // lane base of the warp's shared-memory block: column 0 (y) and column 9 (stage input)
+  double* ws;  // lane base of the warp workspace
   int NV;
   int kidx;
   int phase, stage, j, ind, after_switch;
@@ -55,17 +61,19 @@ struct Lane {
   int status;
   // work counters
   unsigned long long n_derivs, sum_n, n_out;
+#if GC_HOT_IN_SMEM
+  // private copy of the model's hot block (the prefix of DevModel that derivs() and its helpers read): in batch mode
+  // the 32 lanes of a warp belong to 32 different models, so reading the constants from the DevModel array costs 32
+  // cache lines per load; from here it is a conflict-free shared-memory access.
+  double hot[GC_HOT_BYTES / 8];
+#endif
 };
 
-// Column placement.  Default: all ten columns in the warp-interleaved global workspace (12 warps/SM resident).
-// Optional (GALCAMB_EVOLVE_SMEM=1): y (0) and the stage input w9 (9) -- what derivs() reads with latency-critical
-// loads -- in shared memory, the stage derivatives in global memory.  Measured on B200 (profiles/README.md): the
-// shared-memory placement is 1.3x faster per warp but only 4 warps/SM fit, so the global placement wins at
-// every batch size; it stays as a switch for the follow-up work on splitting the state between the two.
-__device__ __forceinline__ double* col(const Lane& L, int c) {
-  if (L.sm && c == 9) return L.sm;
-  return L.ws + (size_t)c * L.NV * GC_LANES;
-}
+// element i of column c of this lane: ws[(c*NV + i-1)*32]  (ws already points at the lane's slot)
+// shared-memory stride between the Lane records of consecutive threads: sizeof(Lane) rounded up to an odd multiple of 8
+#define GC_LANE_STRIDE ((((sizeof(gc::Lane) + 7) / 8) | 1) * 8)
+
+__device__ __forceinline__ double* col(const Lane& L, int c) { return L.ws + (size_t)c * L.NV * GC_LANES; }
 
 // Verner 6(5) stage tableau of camb/subroutines.f90:930-993: w9 = y + temp*(sum_j A[s][j]*w_j), evaluated left to
 // right with the reference's signs so that every partial sum is bit-identical to the Fortran expression.
@@ -504,13 +512,16 @@ __device__ __noinline__ void advance(Lane& L) {
 __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve_sources_kernel(const DevModel* __restrict__ models, const int2* __restrict__ items,
                                                              int nitems, double* __restrict__ workspace, int NV,
                                                              int* __restrict__ status,
-                                                             unsigned long long* __restrict__ counters, int use_smem) {
-  extern __shared__ double gc_smem[];
+                                                             unsigned long long* __restrict__ counters) {
+  // The per-lane control state (layout descriptor EV, dverk communication, pending request) lives in SHARED memory:
+  // as a local variable it is a 1.2 KB stack frame per thread (470 KB per SM at 12 warps), which thrashes L1 and
+  // turned every field access into a long-scoreboard stall.  Stride = odd multiple of 8 B -> conflict-free.
+  extern __shared__ unsigned char gc_smem_raw[];
+  Lane& L = *reinterpret_cast<Lane*>(gc_smem_raw + (size_t)threadIdx.x * GC_LANE_STRIDE);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int gwarp = tid >> 5;
   const bool have = tid < nitems;
-  Lane L;
   L.phase = PH_DONE;
   L.status = 0;
   L.n_derivs = L.sum_n = L.n_out = 0;
@@ -518,10 +529,15 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
     const int2 it = items[tid];
     L.M = models + it.x;
     const DevModel& M = *L.M;
+#if GC_HOT_IN_SMEM
+    {
+      const double* src = reinterpret_cast<const double*>(L.M);
+      for (int i = 0; i < (int)(GC_HOT_BYTES / 8); i++) L.hot[i] = src[i];
+    }
+#endif
     L.kidx = it.y;
     L.NV = NV;
     L.ws = workspace + (size_t)gwarp * GC_NCOL * NV * GC_LANES + lane;
-    L.sm = use_smem ? gc_smem + (size_t)(threadIdx.x >> 5) * NV * GC_LANES + lane : nullptr;
     // DoSourcek, camb/cmbmain.f90:662-689
     L.e.q = M.k[it.y];
     L.e.pig = 0;
@@ -580,7 +596,11 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
     if (!__any_sync(0xffffffffu, need)) break;
 #endif
     if (need) {
+      #if GC_HOT_IN_SMEM
+      derivs(reinterpret_cast<const DevModel*>(L.hot), &L.e, L.req_tau, col(L, L.req_in), col(L, L.req_out));
+#else
       derivs(L.M, &L.e, L.req_tau, col(L, L.req_in), col(L, L.req_out));
+#endif
       L.n_derivs++;
       L.sum_n += L.e.neq;
     }
@@ -607,26 +627,15 @@ extern "C" void gc_upload_constants() {
 
 extern "C" cudaError_t gc_launch_evolve(const DevModel* models, const int2* items, int nitems, double* workspace, int NV,
                                         int* status, unsigned long long* counters, cudaStream_t stream) {
-  static int use_smem = -1;
-  if (use_smem < 0) {
-    const char* e = getenv("GALCAMB_EVOLVE_SMEM");
-    use_smem = (e && atoi(e)) ? 1 : 0;
+  const int threads = GC_EVOLVE_THREADS;
+  const size_t smem = (size_t)threads * GC_LANE_STRIDE;
+  static bool configured = false;
+  if (!configured && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(gc::evolve_sources_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
   }
-  int warps = GC_EVOLVE_THREADS / 32;
-  size_t smem = 0;
-  if (use_smem) {  // 2 columns x NV x 32 lanes x 8 B per warp; as many warps per CTA as fit in 227 KB
-    const size_t per_warp = (size_t)NV * GC_LANES * sizeof(double);
-    while (warps > 1 && warps * per_warp > 227 * 1024) warps--;
-    smem = warps * per_warp;
-    static size_t configured = 0;
-    if (smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(gc::evolve_sources_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      configured = smem;
-    }
-  }
-  const int threads = 32 * warps;
   const int blocks = (nitems + threads - 1) / threads;
-  gc::evolve_sources_kernel<<<blocks, threads, smem, stream>>>(models, items, nitems, workspace, NV, status, counters, use_smem);
+  gc::evolve_sources_kernel<<<blocks, threads, smem, stream>>>(models, items, nitems, workspace, NV, status, counters);
   return cudaGetLastError();
 }
