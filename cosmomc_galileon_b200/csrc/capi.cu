@@ -324,8 +324,11 @@ static int pack_model(int islot, const galcamb_model* m) {
   }
   for (int qn = 0; qn < GC_MAX_NQ; qn++) { D.nu_q[qn] = m->nu_q[qn]; D.nu_int_kernel[qn] = m->nu_int_kernel[qn]; }
   D.dlnam = m->dlnam;
+  D.inv_dlnam = m->dlnam != 0 ? 1.0 / m->dlnam : 0.0;
+  for (int qn = 0; qn < GC_MAX_NQ; qn++) D.inv_nu_q[qn] = m->nu_q[qn] != 0 ? 1.0 / m->nu_q[qn] : 0.0;
   D.nu_tab = g.d_nu_tab;
   D.nthermo = m->nthermo; D.tauminn = m->tauminn; D.dlntau = m->dlntau;
+  D.inv_tauminn = 1.0 / m->tauminn; D.inv_dlntau = 1.0 / m->dlntau;
   D.nt = m->nt; D.nk = m->nk; D.nq = m->nq;
   D.c2 = m->c2; D.c3 = m->c3; D.c4 = m->c4; D.c5 = m->c5; D.cG = m->cG; D.h0 = m->h0; D.orad = m->orad;
   D.ScalarPowerAmp = m->ScalarPowerAmp; D.an = m->an; D.n_run = m->n_run; D.n_runrun = m->n_runrun; D.k_0_scalar = m->k_0_scalar;

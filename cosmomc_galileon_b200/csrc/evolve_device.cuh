@@ -28,7 +28,7 @@ namespace gc {
 #define GC_SP(x) ((double)(x##f))
 
 struct EV {
-  double q, k, k2;
+  double q, k, k2, ik, ik2;  // ik = 1/k, ik2 = 1/k^2 (per-lane constants)
   int w_ix, r_ix, g_ix, polind, nu_pert_ix, nvar, neq;
   int lmaxg, lmaxnr, lmaxnu, lmaxgpol, lmaxnu_pert;
   int nu_ix[GC_MAX_NU], nq[GC_MAX_NU], lmaxnu_tau[GC_MAX_NU];
@@ -54,7 +54,7 @@ __device__ __forceinline__ double herm(double f0, double d0, double f1, double d
 
 // camb/modules.f90:2728-2769
 __device__ inline void thermo(const DevModel& M, double tau, double& cs2b, double& opacity, double* dopacity) {
-  double d = log(tau / M.tauminn) / M.dlntau + 1.0;
+  double d = log(tau * M.inv_tauminn) * M.inv_dlntau + 1.0;
   int i = (int)d;
   d = d - i;
   const int nth = M.nthermo;
@@ -70,7 +70,7 @@ __device__ inline void thermo(const DevModel& M, double tau, double& cs2b, doubl
   const double* r1 = r0 + 5;
   cs2b = herm(r0[0], r0[1], r1[0], r1[1], d);
   opacity = herm(r0[2], r0[3], r1[2], r1[3], d);
-  if (dopacity) *dopacity = herm(r0[3], r0[4], r1[3], r1[4], d) / (tau * M.dlntau);
+  if (dopacity) *dopacity = herm(r0[3], r0[4], r1[3], r1[4], d) * M.inv_dlntau / tau;
 }
 
 // camb/modules.f90:2771-2783 via the running-minimum table (same index as the linear scan)
@@ -110,7 +110,7 @@ __device__ inline void Nu_background(const DevModel& M, double am, double& rhonu
     pnu = 900.0 / 120.0 / GC_NU_CONST * (GC_ZETA5 - 63.0 / 4 * GC_ZETA7 / (am * am)) / am;
     return;
   }
-  double d = log(am / GC_AM_MIN) / M.dlnam + 1.0;
+  double d = log(am * 100.0) * M.inv_dlnam + 1.0;
   int i = (int)d;
   d = d - i;
   const double* r0 = M.nu_tab + (size_t)(i - 1) * 6;
@@ -123,7 +123,7 @@ __device__ inline void Nu_background(const DevModel& M, double am, double& rhonu
 __device__ inline double Nu_drho(const DevModel& M, double am, double adotoa, double rhonu) {
   if (am < GC_AM_MINP) return 2 * GC_NU_CONST2 * am * am * adotoa;
   if (am > GC_AM_MAXP) return 3 / (2 * GC_NU_CONST) * (GC_ZETA3 * am - (15 * GC_ZETA5) / 2 / am) * adotoa;
-  double d = log(am / GC_AM_MIN) / M.dlnam + 1.0;
+  double d = log(am * 100.0) * M.inv_dlnam + 1.0;
   int i = (int)d;
   d = d - i;
   const double* r0 = M.nu_tab + (size_t)(i - 1) * 6;
@@ -136,7 +136,7 @@ __device__ inline double Nu_dp(const DevModel& M, double am, double adotoa, doub
   if (am < GC_AM_MINP) return 2 * adotoa * (1.0 - GC_NU_CONST2 * am * am) / 3.0 - 4.0 / 3.0 * adotoa;
   if (am > GC_AM_MAXP)
     return -900.0 / 120.0 / GC_NU_CONST * (GC_ZETA5 - 189.0 / 4 * GC_ZETA7 / (am * am)) * adotoa / am;
-  double d = log(am / GC_AM_MIN) / M.dlnam + 1.0;
+  double d = log(am * 100.0) * M.inv_dlnam + 1.0;
   int i = (int)d;
   d = d - i;
   const double* r0 = M.nu_tab + (size_t)(i - 1) * 6;
@@ -151,22 +151,41 @@ __device__ inline void gal_HX(const DevModel& M, double a, double& hbar, double&
   int i = (int)(log(a / M.gal_a0) * M.gal_lnq_inv);
   if (i < 0) i = 0;
   if (i > n - 2) i = n - 2;
-  while (i > 0 && M.gal[(size_t)i * 5] > a) i--;
-  while (i < n - 2 && M.gal[(size_t)(i + 1) * 5] <= a) i++;
+  // The grid is geometric, so the guess is the bisection result except within rounding of a node.  Load both rows
+  // of the guessed interval at once (ten independent loads, one memory latency) and only fall back to the
+  // dependent-load search when the bracket test fails.
   const double* r0 = M.gal + (size_t)i * 5;
   const double* r1 = r0 + 5;
-  const double dx = r1[0] - r0[0], delx = a - r0[0];
+  double v0[5], v1[5];
+#pragma unroll
+  for (int c = 0; c < 5; c++) {
+    v0[c] = r0[c];
+    v1[c] = r1[c];
+  }
+  if (!(v0[0] <= a && (a < v1[0] || i == n - 2))) {
+    while (i > 0 && M.gal[(size_t)i * 5] > a) i--;
+    while (i < n - 2 && M.gal[(size_t)(i + 1) * 5] <= a) i++;
+    r0 = M.gal + (size_t)i * 5;
+    r1 = r0 + 5;
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+      v0[c] = r0[c];
+      v1[c] = r1[c];
+    }
+  }
+  const double dx = v1[0] - v0[0], delx = a - v0[0];
+  const double idx = 1.0 / dx, third = 1.0 / 3.0;
   {
-    const double dy = r1[1] - r0[1];
-    const double b = (dy / dx) - dx * (r1[2] + 2.0 * r0[2]) / 3.0;
-    const double dd = (r1[2] - r0[2]) / (3.0 * dx);
-    hbar = r0[1] + delx * (b + delx * (r0[2] + delx * dd));
+    const double dy = v1[1] - v0[1];
+    const double b = dy * idx - dx * (v1[2] + 2.0 * v0[2]) * third;
+    const double dd = (v1[2] - v0[2]) * idx * third;
+    hbar = v0[1] + delx * (b + delx * (v0[2] + delx * dd));
   }
   {
-    const double dy = r1[3] - r0[3];
-    const double b = (dy / dx) - dx * (r1[4] + 2.0 * r0[4]) / 3.0;
-    const double dd = (r1[4] - r0[4]) / (3.0 * dx);
-    xgal = a * (r0[3] + delx * (b + delx * (r0[4] + delx * dd)));
+    const double dy = v1[3] - v0[3];
+    const double b = dy * idx - dx * (v1[4] + 2.0 * v0[4]) * third;
+    const double dd = (v1[4] - v0[4]) * idx * third;
+    xgal = a * (v0[3] + delx * (b + delx * (v0[4] + delx * dd)));
   }
 }
 
@@ -701,10 +720,11 @@ __device__ inline void Nu_Integrate_L012(const DevModel& M, const EV& e, const d
   const double am = a * M.nu_masses[nu_i];
   int ind = e.nu_ix[nu_i];
   for (int iq = 1; iq <= e.nq[nu_i]; iq++) {
-    const double aq = am / M.nu_q[iq - 1];
-    const double v = 1.0 / sqrt(1.0 + aq * aq);
+    const double aq = am * M.inv_nu_q[iq - 1];
+    const double e2 = 1.0 + aq * aq;
+    const double v = rsqrt(e2), iv = e2 * v;  // v = q/E, 1/v = E/q
     const double ker = M.nu_int_kernel[iq - 1];
-    drhonu = drhonu + ker * AT(y, ind) / v;
+    drhonu = drhonu + ker * AT(y, ind) * iv;
     fnu = fnu + ker * AT(y, ind + 1);
     if (dpnu) {
       *dpnu = *dpnu + ker * AT(y, ind) * v;
@@ -714,13 +734,14 @@ __device__ inline void Nu_Integrate_L012(const DevModel& M, const EV& e, const d
   }
   ind = e.nu_pert_ix;
   for (int iq = e.nq[nu_i] + 1; iq <= M.nqmax; iq++) {
-    const double aq = am / M.nu_q[iq - 1];
-    const double v = 1.0 / sqrt(1.0 + aq * aq);
-    const double r = M.nu_masses[nu_i] / M.nu_q[iq - 1];
+    const double aq = am * M.inv_nu_q[iq - 1];
+    const double e2 = 1.0 + aq * aq;
+    const double v = rsqrt(e2), iv = e2 * v;
+    const double r = M.nu_masses[nu_i] * M.inv_nu_q[iq - 1];
     const double pert_scale = (r * r) / 2;
     const double ker = M.nu_int_kernel[iq - 1];
     const double tmp = ker * (AT(y, e.r_ix) + pert_scale * AT(y, ind));
-    drhonu = drhonu + tmp / v;
+    drhonu = drhonu + tmp * iv;
     fnu = fnu + ker * (AT(y, e.r_ix + 1) + pert_scale * AT(y, ind + 1));
     if (dpnu) {
       *dpnu = *dpnu + tmp * v;
@@ -786,15 +807,16 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
   const DevModel& M = *Mp;
   EV& e = *ep;
   const bool gal = M.use_galileon != 0;
-  const double k = e.k, k2 = e.k2;
+  const double k = e.k, ik = e.ik, ik2 = e.ik2;
   const double a = AT(ay, 1), a2 = a * a;
+  const double ia = 1.0 / a, ia2 = ia * ia;
   const double etak = AT(ay, 2), clxc = AT(ay, 3), clxb = AT(ay, 4), vb = AT(ay, 5);
   double dphi = 0, dphiprime = 0;
   if (gal) {
     dphi = AT(ay, e.w_ix);
     dphiprime = AT(ay, e.w_ix + 1);
   }
-  const double grhob_t = M.grhob / a, grhoc_t = M.grhoc / a, grhor_t = M.grhornomass / a2, grhog_t = M.grhog / a2;
+  const double grhob_t = M.grhob * ia, grhoc_t = M.grhoc * ia, grhor_t = M.grhornomass * ia2, grhog_t = M.grhog * ia2;
   // massive-neutrino background at this a (shared by MassiveNuVars, GetdHdX and dtauda)
   double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
   for (int i = 0; i < M.n_eig; i++) Nu_background(M, a * M.nu_masses[i], rhonu[i], pnu[i]);
@@ -824,15 +846,16 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
   double wnu_arr[GC_MAX_NU];
   if (M.Num_Nu_massive > 0) {  // MassiveNuVars, :1209-1252
     for (int nu_i = 0; nu_i < M.n_eig; nu_i++) {
-      const double grhormass_t = M.grhormass[nu_i] / (a * a);
+      const double grhormass_t = M.grhormass[nu_i] * ia2;
+      const double irho = 1.0 / rhonu[nu_i];
       double clxnu, qnu;
       if (e.MassiveNuApprox[nu_i]) {
         clxnu = AT(ay, e.nu_ix[nu_i]);
         qnu = AT(ay, e.nu_ix[nu_i] + 2);
       } else {
         Nu_Integrate_L012(M, e, ay, a, nu_i, clxnu, qnu, nullptr, nullptr);
-        qnu = qnu / rhonu[nu_i];
-        clxnu = clxnu / rhonu[nu_i];
+        qnu = qnu * irho;
+        clxnu = clxnu * irho;
       }
       const double grhonu_t = grhormass_t * rhonu[nu_i];
       const double gpnu_t = grhormass_t * pnu[nu_i];
@@ -840,7 +863,7 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
       gpres = gpres + gpnu_t;
       dgrho_matter = dgrho_matter + grhonu_t * clxnu;
       dgq = dgq + grhonu_t * qnu;
-      wnu_arr[nu_i] = pnu[nu_i] / rhonu[nu_i];
+      wnu_arr[nu_i] = pnu[nu_i] * irho;
     }
   }
   // dtauda(a), :107-156
@@ -854,20 +877,21 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
     if (M.Num_Nu_massive != 0)
       for (int nu_i = 0; nu_i < M.n_eig; nu_i++) grhoa2 = grhoa2 + rhonu[nu_i] * M.grhormass[nu_i];
   }
-  const double adotoa = 1. / (a * sqrt(3 / grhoa2));
+  const double adotoa = sqrt(grhoa2 * (1.0 / 3.0)) * ia;  // 1/(a dtauda(a))
+  const double iadotoa = 1.0 / adotoa;
   const double cothxor = 1.0 / tau;
   double dgrho = dgrho_matter;
   double z = 0, dz, clxr, qr, pir, clxg, qg, pig = 0, dgrhogal_t;
   if (e.no_nu) {
     if (gal) {
       dgrhogal_t = gal_fast_Chigal(F, dgrho, etak, dphi, dphiprime);
-      z = (0.5 * (dgrho + dgrhogal_t) / k + etak) / adotoa;
-      dz = -adotoa * z - 0.5 * (dgrho + dgrhogal_t) / k;
+      z = (0.5 * (dgrho + dgrhogal_t) * ik + etak) * iadotoa;
+      dz = -adotoa * z - 0.5 * (dgrho + dgrhogal_t) * ik;
     } else {
-      z = (0.5 * dgrho / k + etak) / adotoa;
-      dz = -adotoa * z - 0.5 * dgrho / k;
+      z = (0.5 * dgrho * ik + etak) * iadotoa;
+      dz = -adotoa * z - 0.5 * dgrho * ik;
     }
-    clxr = -4 * dz / k;
+    clxr = -4 * dz * ik;
     qr = -4.0 / 3 * z;
     pir = 0;
   } else {
@@ -879,16 +903,16 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
     if (!e.no_nu) {
       if (gal) {
         dgrhogal_t = gal_fast_Chigal(F, dgrho, etak, dphi, dphiprime);
-        z = (0.5 * (dgrho + dgrhogal_t) / k + etak) / adotoa;
-        dz = -adotoa * z - 0.5 * (dgrho + dgrhogal_t) / k;
+        z = (0.5 * (dgrho + dgrhogal_t) * ik + etak) * iadotoa;
+        dz = -adotoa * z - 0.5 * (dgrho + dgrhogal_t) * ik;
       } else {
-        z = (0.5 * dgrho / k + etak) / adotoa;
-        dz = -adotoa * z - 0.5 * dgrho / k;
+        z = (0.5 * dgrho * ik + etak) * iadotoa;
+        dz = -adotoa * z - 0.5 * dgrho * ik;
       }
-      clxg = -4 * dz / k - 4 / k * opacity * (vb + z);
+      clxg = -4 * dz * ik - 4 * ik * opacity * (vb + z);
       qg = -4.0 / 3 * z;
     } else {
-      clxg = clxr - 4 / k * opacity * (vb + z);
+      clxg = clxr - 4 * ik * opacity * (vb + z);
       qg = qr;
     }
     pig = 0;
@@ -907,8 +931,8 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
     dgrho = dgrho + dgrhogal_t;
     dgq = dgq + gal_fast_qgal(F, dgq, dphi, dphiprime);
   }
-  z = (0.5 * dgrho / k + etak) / adotoa;
-  const double sigma = (z + 1.5 * dgq / k2);
+  z = (0.5 * dgrho * ik + etak) * iadotoa;
+  const double sigma = (z + 1.5 * dgq * ik2);
   AT(ayp, 2) = 0.5 * dgq;
   const double clxcdot = -k * z;
   AT(ayp, 3) = clxcdot;
@@ -918,21 +942,23 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
   double vbdot, qgdot, pigdot;
   if (e.TightCoupling) {
     const double adotdota = (adotoa * adotoa - gpres) / 2;
-    pig = 32.0 / 45 / opacity * k * (sigma + vb);
-    const double slip = -(2 * adotoa / (1 + pb43) + dopacity / opacity) * (vb - 3.0 / 4 * qg) +
-                        (-adotdota * vb - k / 2 * adotoa * clxg + k * (cs2 * clxbdot - clxgdot / 4)) / (opacity * (1 + pb43));
+    const double iop = 1.0 / opacity, iop2 = iop * iop, ipb = 1.0 / (1 + pb43);
+    const double c3245 = 32.0 / 45.0;
+    pig = c3245 * iop * k * (sigma + vb);
+    const double slip = -(2 * adotoa * ipb + dopacity * iop) * (vb - 3.0 / 4 * qg) +
+                        (-adotdota * vb - k / 2 * adotoa * clxg + k * (cs2 * clxbdot - clxgdot / 4)) * (iop * ipb);
     double dgs = grhog_t * pig + grhor_t * pir;
     if (gal) dgs = dgs + gal_fast_Pigal(GC, F, dgrho, dgq, dgs, etak, dphi);
-    const double sigmadot = -2 * adotoa * sigma - dgs / k + etak;
+    const double sigmadot = -2 * adotoa * sigma - dgs * ik + etak;
     qgdot = k * (clxg / 4.0 - pig / 2.0) + opacity * slip;
-    const double op2 = opacity * opacity;
-    pig = 32.0 / 45 / opacity * k * (sigma + 3.0 * qg / 4.0) * (1 + (dopacity * 11.0 / 6.0 / op2)) +
-          (32.0 / 45.0 / op2) * k * (sigmadot + 3.0 * qgdot / 4.0) * (-11.0 / 6.0);
-    pigdot = -(32.0 / 45.0) * (dopacity / op2) * k * (sigma + 3.0 * qg / 4.0) * (1 + dopacity * 11.0 / 6.0 / op2) +
-             (32.0 / 45.0 / opacity) * k * (sigmadot + 3.0 * qgdot / 4.0) * (1 + (11.0 / 6.0) * (dopacity / op2));
+    const double dop = dopacity * iop2;
+    pig = c3245 * iop * k * (sigma + 3.0 * qg / 4.0) * (1 + (dop * (11.0 / 6.0))) +
+          (c3245 * iop2) * k * (sigmadot + 3.0 * qgdot / 4.0) * (-11.0 / 6.0);
+    pigdot = -c3245 * dop * k * (sigma + 3.0 * qg / 4.0) * (1 + dop * (11.0 / 6.0)) +
+             (c3245 * iop) * k * (sigmadot + 3.0 * qgdot / 4.0) * (1 + (11.0 / 6.0) * dop);
     e.pigdot = pigdot;
-    vbdot = (-adotoa * vb + cs2 * k * clxb + k / 4 * pb43 * (clxg - 2 * 1.0 * pig)) / (1 + pb43);
-    vbdot = vbdot + pb43 / (1 + pb43) * slip;
+    vbdot = (-adotoa * vb + cs2 * k * clxb + k / 4 * pb43 * (clxg - 2 * 1.0 * pig)) * ipb;
+    vbdot = vbdot + pb43 * ipb * slip;
     e.pig = pig;
   } else {
     vbdot = -adotoa * vb + cs2 * k * clxb - photbar * opacity * (4.0 / 3 * vb - qg);
@@ -1006,8 +1032,9 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
   if (M.Num_Nu_massive == 0) return;
   for (int nu_i = 0; nu_i < M.n_eig; nu_i++) {
     if (e.MassiveNuApprox[nu_i]) {
-      const double G11_t = e.G11[nu_i] / a / a2;
-      const double G30_t = e.G30[nu_i] / a / a2;
+      const double ia3 = ia * ia2;
+      const double G11_t = e.G11[nu_i] * ia3;
+      const double G30_t = e.G30[nu_i] * ia3;
       const int o = e.nu_ix[nu_i];
       const double w = wnu_arr[nu_i];
       AT(ayp, o) = -k * z * (w + 1) + 3 * adotoa * (w * AT(ay, o) - AT(ay, o + 1)) - k * AT(ay, o + 2);
@@ -1017,9 +1044,8 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
     } else {
       int ind = e.nu_ix[nu_i];
       for (int i = 1; i <= e.nq[nu_i]; i++) {
-        const double qq = M.nu_q[i - 1];
-        const double aq = a * M.nu_masses[nu_i] / qq;
-        const double v = 1.0 / sqrt(1.0 + aq * aq);
+        const double aq = a * M.nu_masses[nu_i] * M.inv_nu_q[i - 1];
+        const double v = rsqrt(1.0 + aq * aq);
         AT(ayp, ind) = -k * (4.0 / 3.0 * z + v * AT(ay, ind + 1));
         ind = ind + 1;
         AT(ayp, ind) = v * (denlk(e, 1) * AT(ay, ind - 1) - denlk2(e, 1) * AT(ay, ind + 1));
@@ -1263,6 +1289,8 @@ __device__ __noinline__ void output_sources(const DevModel* __restrict__ Mp, con
 __device__ inline void initial(const DevModel& M, EV& e, double* y, double tau) {
   e.k = e.q;
   e.k2 = e.q * e.q;
+  e.ik = 1.0 / e.k;
+  e.ik2 = e.ik * e.ik;
   const double k = e.k;
   double ep;
   const double ep0 = 1.0e-2;

@@ -37,6 +37,8 @@ struct DevModel {
   double grhom, grhog, grhor, grhob, grhoc, grhov, grhornomass, grhok;   // camb/modules.f90:171-193
   double c2, c3, c4, c5, cG, h0, orad;                                   // camb/galileon.cc:80-92
   double tauminn, dlntau, dlnam;
+  double inv_tauminn, inv_dlntau, inv_dlnam;  // reciprocals used by the table-index computations
+  double inv_nu_q[GC_MAX_NQ];
   double gal_lnq_inv, gal_a0;  // index guess into the background table: i ~ log(a/a0)*gal_lnq_inv
   double grhormass[GC_MAX_NU], nu_masses[GC_MAX_NU];
   double nu_q[GC_MAX_NQ], nu_int_kernel[GC_MAX_NQ];
