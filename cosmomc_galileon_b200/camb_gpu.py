@@ -259,8 +259,15 @@ class GalCamb:
         lmax = models[0].d["lmax"]
         if out is None:
             out = np.zeros((n, 3, lmax - 1))
-        self._chk(self.L.galcamb_batch_cls_(arr, C.byref(_I(n)), out.ctypes.data))
+        rc = self.L.galcamb_batch_cls_(arr, C.byref(_I(n)), out.ctypes.data)
+        if rc not in (0, 4):  # 4 = error_evolution in some slots: their rows are NaN, see status()
+            self._chk(rc)
         return out
+
+    def status(self, slot=0):
+        st = _I(0)
+        self._chk(self.L.galcamb_get_status_(C.byref(_I(slot)), C.byref(st)))
+        return st.value
 
     def timings(self):
         ms = np.zeros(8)

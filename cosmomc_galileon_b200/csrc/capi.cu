@@ -653,14 +653,21 @@ int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* 
     for (int i = 0; i < n; i++)
       if ((rc = upload_model(i, &models[i]))) return rc;
   }
-  if ((rc = galcamb_evolve_sources_())) return rc;
+  // A parameter point whose integration fails (CAMB error_evolution) must not sink the batch: its slot keeps the
+  // error id (galcamb_get_status_), its C_l come back as NaN, the other points are unaffected (CosmoMC rejects
+  // such points one by one, source/Calculator_CAMB.f90:235-243).
+  const int rc_ev = galcamb_evolve_sources_();
+  if (rc_ev != 0 && rc_ev != 4) return rc_ev;
   if ((rc = galcamb_los_integrate_())) return rc;
   if ((rc = galcamb_scalar_cls_())) return rc;
   const size_t per = (size_t)3 * (models[0].lmax - 1);
   for (int i = 0; i < *nmodels; i++)
     CK(cudaMemcpyAsync(Cl_out + per * i, g.slots[i].host.Cl, per * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
-  return 0;
+  for (int i = 0; i < *nmodels; i++)
+    if (g.slots[i].status)
+      for (size_t j = 0; j < per; j++) Cl_out[per * i + j] = std::nan("");
+  return rc_ev;
 }
 
 int galcamb_get_timings_(double* ms) {

@@ -133,6 +133,28 @@ def test_golden_fixture_and_batch(gpu):
     assert relmax(D, gold["Delta_q"]) < TOL_TRANSFER
 
 
+def test_heterogeneous_batch(gpu):
+    """A batch of DIFFERENT cosmologies (LCDM, the Galileon point, a shifted Galileon point: different k and time
+    grids, mixed use_galileon inside one warp) -- every slot must match its own oracle run."""
+    from oracle_py import Oracle
+    from tables_from_oracle import tables_from_oracle
+    GAL2 = dict(GAL, H0=78.2, ombh2=0.02225, optical_depth=0.08, an=0.955)  # (the test point sits close to the no-ghost boundary: larger shifts are rejected by galileon.cc:209-242)
+    runs = []
+    for P in (LCDM, GAL, GAL2):
+        o = Oracle(**P)
+        o.run()
+        runs.append((o, tables_from_oracle(o, P)))
+    assert len({t.d["nk"] for _, t in runs} | {t.d["nt"] for _, t in runs}) > 2  # the grids really differ
+    t0 = runs[0][1]
+    gpu.InitSpherBessels(t0.ls, max(t.d["kmaxfile"] for _, t in runs), 1.0)
+    out = gpu.batch_cls([t for _, t in runs])
+    for i, (o, t) in enumerate(runs):
+        assert gpu.status(i) == 0
+        assert np.max(np.abs(out[i] / o.Cl()[:3] - 1)) < TOL_CL
+        assert relmax(gpu.Src(i), o.Src()) < TOL_TRANSFER
+        assert relmax(gpu.Delta_p_l_k(i), o.Delta()) < TOL_TRANSFER
+
+
 def test_primordial_rescaling_property(gpu):
     """C_l is linear in A_s (size-independent property of the K4 stage): doubling ScalarPowerAmp doubles iCl."""
     from cosmomc_galileon_b200 import ModelTables
