@@ -277,7 +277,9 @@ def main():
             "roofline": {"kernel": "evolve_sources_kernel", "bound": "fp64", "achieved": flop / t_ev / 1e12, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": flop / t_ev / 1e12 / fp64_peak,
                          "peak_source": "measured: galcamb_fp64_peak_ DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure; nominal 37.2)",
-                         "traffic": None, "share_of_step": ev["evolve"] / (ev["evolve"] + ev["spline_k"] + ev["los"] + ev["cls"]),
+                         "traffic": 5.19e9 * B, "traffic_source": "dram__bytes.sum of the ncu capture profiles/r1_evolve_b448_final_sections "
+                         "(768 GB/s x 3.025 s / 448 spectra = 5.19 GB per spectrum), scaled to this batch; bytes, per launch",
+                         "share_of_step": ev["evolve"] / (ev["evolve"] + ev["spline_k"] + ev["los"] + ev["cls"]),
                          "flop_per_spectrum": meta["flop_ode"], "ms_per_launch": 1e3 * t_ev},
             "roofline_los": {"kernel": "los_kernel", "bound": "hbm", "achieved": meta["bytes_los_operand"] * B / t_los / 1e9,
                              "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
