@@ -140,6 +140,25 @@ __device__ __forceinline__ void stage_input(Lane& L, int row, int n, double temp
   }
 }
 
+// The stage derivatives w2..w8 and the stage input w9 are dead once a trial step has been accepted or rejected;
+// they will be rewritten before they are read again.  Dropping their (dirty) lines from L2 without write-back keeps
+// the dead 70 % of the workspace from being streamed to HBM and from competing with live lines for L2 capacity.
+// One 256-byte row per element = two 128-byte lines; lanes 0 and 16 issue the discard for "their" line.
+#ifndef GC_DISCARD_DEAD
+#define GC_DISCARD_DEAD 1
+#endif
+// A line holds the same element of 16 lanes, so it may only be dropped when all 16 lanes of that half-warp are at
+// this very point of their trial step together (true in lock-step batches; otherwise the lines are simply kept).
+__device__ __forceinline__ void discard_rows(const double* colp, int n) {
+#if GC_DISCARD_DEAD
+  const unsigned grp = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
+  const bool together = (__activemask() & grp) == grp;
+  if (together && (threadIdx.x & 15) == 0) {
+    for (int i = 1; i <= n; i++) asm volatile("discard.global.L2 [%0], 128;" ::"l"(&AT(colp, i)) : "memory");
+  }
+#endif
+}
+
 struct Switches {
   double ktau, no_nu, no_phot, nu_massless, nu_nonrel, nu_massive, next;
 };
@@ -462,10 +481,13 @@ __device__ __noinline__ void advance(Lane& L) {
         L.est = errn * L.hmag * 1.0;
         L.ind = 5;
         if (L.est > tol) L.ind = 6;
+        for (int c = 2; c <= 8; c++) discard_rows(col(L, c), n);
         if (L.ind != 6) {
           L.tau = L.xtrial;
           double* yw = col(L, 0);
           for (int i = 1; i <= n; i++) AT(yw, i) = AT(w9, i);
+          discard_rows(w9, n);
+          discard_rows(col(L, 1), n);  // k1 is re-evaluated at the start of the next step
           L.nfail = 0.0;
           if (L.tau == L.target) {
             L.ind = 3;
@@ -475,6 +497,7 @@ __device__ __noinline__ void advance(Lane& L) {
             break;
           }
         } else {
+          discard_rows(w9, n);
           L.nfail = L.nfail + 1.0;
           if (!(L.hmag > L.hmin)) {
             L.status = 4;  // dverk ind=-3 -> error_evolution (camb/equations_galileon.f90:285-292)

@@ -155,6 +155,40 @@ def test_heterogeneous_batch(gpu):
         assert relmax(gpu.Delta_p_l_k(i), o.Delta()) < TOL_TRANSFER
 
 
+def test_massless_neutrino_model(gpu):
+    """No massive eigenstate (omnuh2 = 0 -> Num_Nu_massive = 0, camb/modules.f90:307-316): the neutrino blocks of the
+    state vector and the table lookups disappear."""
+    from oracle_py import Oracle
+    from tables_from_oracle import tables_from_oracle
+    P = dict(ombh2=0.0226, omch2=0.112, omnuh2=0.0, H0=70.0)
+    o = Oracle(lmax=1200, **P)
+    o.run()
+    assert o.geti("Num_Nu_massive") == 0
+    t = tables_from_oracle(o, P, lmax=1200)
+    run_gpu(gpu, t)
+    assert relmax(gpu.Src(), o.Src()) < TOL_TRANSFER
+    _, cl = gpu.Cls()
+    assert np.max(np.abs(cl / o.Cl() - 1)) < TOL_CL
+
+
+def test_failed_point_does_not_sink_the_batch(gpu):
+    """Error behaviour: a point whose integration cannot proceed (here: a repeated output time, which dverk rejects
+    like the reference's 'x = xend' error, camb/subroutines.f90:700-715) gets CAMB's error_evolution id and NaN C_l;
+    the other points of the batch are unaffected."""
+    from cosmomc_galileon_b200 import ModelTables
+    t = ModelTables.load(os.path.join(GOLD, "config2_tables.npz"))
+    gold = np.load(os.path.join(GOLD, "config2_golden.npz"))
+    gpu.InitSpherBessels(t.ls, t.d["kmaxfile"], 1.0)
+    tau = t.d["tau"].copy()
+    tau[40] = tau[39]
+    bad = t.copy(tau=tau)
+    out = gpu.batch_cls([t.copy(), bad, t.copy()])
+    assert gpu.status(0) == 0 and gpu.status(2) == 0 and gpu.status(1) == 4
+    assert np.all(np.isnan(out[1]))
+    for i in (0, 2):
+        assert np.max(np.abs(out[i] / gold["Cl"] - 1)) < TOL_CL
+
+
 def test_primordial_rescaling_property(gpu):
     """C_l is linear in A_s (size-independent property of the K4 stage): doubling ScalarPowerAmp doubles iCl."""
     from cosmomc_galileon_b200 import ModelTables
