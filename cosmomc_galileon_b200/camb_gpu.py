@@ -139,9 +139,15 @@ def load_library():
     global _lib
     if _lib is None:
         p = lib_path()
+        if not os.path.exists(p) and not os.environ.get("GALCAMB_LIB"):
+            try:  # the .so is a build artefact (git-ignored): compile it in place when nvcc is around
+                from . import build as _build
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise RuntimeError("libgalcamb_b200.so is not built and could not be built (%s); there is no CPU "
+                                   "fallback" % e)
         if not os.path.exists(p):
-            raise RuntimeError("libgalcamb_b200.so is not built (run `python cosmomc_galileon_b200/build.py`); "
-                               "there is no CPU fallback")
+            raise RuntimeError("libgalcamb_b200.so not found at %s; there is no CPU fallback" % p)
         L = C.CDLL(p)
         L.galcamb_init_.argtypes = [C.POINTER(_I)]
         L.galcamb_last_error_.restype = C.c_char_p

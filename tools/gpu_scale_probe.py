@@ -1,9 +1,10 @@
-"""Scratch: stage timings vs batch size (replicas of the config-2 table fixture)."""
+"""Tool: stage timings vs batch size (replicas of the config-2 table fixture).  usage: gpu_scale_probe.py 32 256 1024"""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import numpy as np
 from cosmomc_galileon_b200 import GalCamb, ModelTables
-H = os.path.dirname(os.path.abspath(__file__))
+H = os.path.join(ROOT, "tests")
 t = ModelTables.load(os.path.join(H, "golden", "config2_tables.npz"))
 g = GalCamb(0)
 tmpl = np.fromfile(os.path.join(H, "golden", "highL_template.f64")).reshape(7999, 4)[:, :3].T.copy()

@@ -1,7 +1,8 @@
-"""Scratch GPU bring-up script (not a pytest): oracle vs CUDA stage by stage."""
+"""GPU bring-up tool (not a pytest): oracle vs CUDA stage by stage, with timings.  Uses the test oracle."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from oracle_py import Oracle, LCDM
 from tables_from_oracle import tables_from_oracle
@@ -15,7 +16,7 @@ def rel(a, b):
     return np.max(np.abs(a - b)) / s
 
 g = GalCamb(0)
-tmpl = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "highL_template.f64")).reshape(7999, 4)[:, :3].T.copy()
+tmpl = np.fromfile(os.path.join(ROOT, "tests", "golden", "highL_template.f64")).reshape(7999, 4)[:, :3].T.copy()
 g.set_template(tmpl)
 for name, P in (("LCDM", LCDM), ("GAL", GAL)):
     o = Oracle(**P)
