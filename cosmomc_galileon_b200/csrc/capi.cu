@@ -489,9 +489,13 @@ int galcamb_evolve_sources_(void) {
     order = e ? atoi(e) : 0;
   }
   if (order == 0) {
-    for (int kk = 0; kk < max_nk; kk++)
+    // every k index starts on a warp boundary (padding items have model = -1): a warp never mixes different k, whose
+    // step sequences and switch times differ -- mixing them costs 2-4x (a single model is 197 one-lane warps)
+    for (int kk = 0; kk < max_nk; kk++) {
       for (int m = 0; m < nm; m++)
         if (kk < g.slots[m].host.nk) g.items.push_back(make_int2(m, kk));
+      while (g.items.size() % 32) g.items.push_back(make_int2(-1, -1));
+    }
   } else {
     // warps of 32 adjacent k of ONE model (constants warp-uniform), dealt low-k-first across models
     for (int k0 = 0; k0 < max_nk; k0 += 32)
@@ -527,7 +531,7 @@ int galcamb_evolve_sources_(void) {
   g.counters[2] = (double)c[2];
   int rc = 0;
   for (int i = 0; i < nitems; i++)
-    if (st[i]) {
+    if (st[i] && g.items[i].x >= 0) {
       g.slots[g.items[i].x].status = st[i] >= 100 ? 4 : st[i];
       rc = 4;  // error_evolution
       char buf[160];

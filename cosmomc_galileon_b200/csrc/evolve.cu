@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int gwarp = tid >> 5;
-  const bool have = tid < nitems;
+  const bool have = tid < nitems && items[tid < nitems ? tid : 0].x >= 0;  // padding items carry model = -1
   L.phase = PH_DONE;
   L.status = 0;
   L.n_derivs = L.sum_n = L.n_out = 0;
@@ -613,11 +613,11 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
   for (;;) {
     if (L.phase != PH_DONE) advance(L);
     const bool need = L.phase != PH_DONE;
-#if GC_EVOLVE_THREADS > 32
-    if (!__syncthreads_or(need)) break;
-#else
-    if (!__any_sync(0xffffffffu, need)) break;
-#endif
+    if (blockDim.x > 32) {
+      if (!__syncthreads_or(need)) break;
+    } else {
+      if (!__any_sync(0xffffffffu, need)) break;
+    }
     if (need) {
       #if GC_HOT_IN_SMEM
       derivs(reinterpret_cast<const DevModel*>(L.hot), &L.e, L.req_tau, col(L, L.req_in), col(L, L.req_out));
@@ -628,6 +628,7 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
       L.sum_n += L.e.neq;
     }
   }
+  if (tid < nitems && !have) status[tid] = 0;
   if (have) {
     status[tid] = L.status;
     atomicAdd(&counters[0], L.n_derivs);
@@ -650,15 +651,18 @@ extern "C" void gc_upload_constants() {
 
 extern "C" cudaError_t gc_launch_evolve(const DevModel* models, const int2* items, int nitems, double* workspace, int NV,
                                         int* status, unsigned long long* counters, cudaStream_t stream) {
-  const int threads = GC_EVOLVE_THREADS;
-  const size_t smem = (size_t)threads * GC_LANE_STRIDE;
+  // Few work items (a single model = ~200 items): one warp per CTA so that every warp gets an SM to itself and no
+  // warp waits for another at the lock-step barrier; the run time is then the critical path of one low-k item.
+  const int threads = nitems <= 148 * 64 ? 32 : GC_EVOLVE_THREADS;
+  const size_t smem = (size_t)GC_EVOLVE_THREADS * GC_LANE_STRIDE;  // same carve-out for both shapes
   static bool configured = false;
-  if (!configured && smem > 48 * 1024) {
+  if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gc::evolve_sources_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int blocks = (nitems + threads - 1) / threads;
-  gc::evolve_sources_kernel<<<blocks, threads, smem, stream>>>(models, items, nitems, workspace, NV, status, counters);
+  gc::evolve_sources_kernel<<<blocks, threads, (size_t)threads * GC_LANE_STRIDE, stream>>>(models, items, nitems, workspace, NV, status,
+                                                                                          counters);
   return cudaGetLastError();
 }
