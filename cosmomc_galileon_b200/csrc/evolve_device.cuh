@@ -816,6 +816,25 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
     dphi = AT(ay, e.w_ix);
     dphiprime = AT(ay, e.w_ix + 1);
   }
+  // issue the loads of the low multipoles now: they are independent and their (L2) latencies then overlap with the
+  // table lookups below instead of being paid one by one where each value is first used
+  double y_r0 = 0, y_r1 = 0, y_r2 = 0, y_g0 = 0, y_g1 = 0, y_g2 = 0, y_g3 = 0, y_e2 = 0, y_e3 = 0, y_r3 = 0;
+  if (!e.no_nu) {
+    y_r0 = AT(ay, e.r_ix);
+    y_r1 = AT(ay, e.r_ix + 1);
+    y_r2 = AT(ay, e.r_ix + 2);
+    if (!e.high_ktau && e.lmaxnr > 2) y_r3 = AT(ay, e.r_ix + 3);
+  }
+  if (!e.no_phot) {
+    y_g0 = AT(ay, e.g_ix);
+    y_g1 = AT(ay, e.g_ix + 1);
+    if (!e.TightCoupling) {
+      y_g2 = AT(ay, e.g_ix + 2);
+      if (e.lmaxg > 2) y_g3 = AT(ay, e.g_ix + 3);
+      y_e2 = AT(ay, e.polind + 2);
+      if (e.lmaxgpol > 2) y_e3 = AT(ay, e.polind + 3);
+    }
+  }
   const double grhob_t = M.grhob * ia, grhoc_t = M.grhoc * ia, grhor_t = M.grhornomass * ia2, grhog_t = M.grhog * ia2;
   // massive-neutrino background at this a (shared by MassiveNuVars, GetdHdX and dtauda)
   double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
@@ -895,9 +914,9 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
     qr = -4.0 / 3 * z;
     pir = 0;
   } else {
-    clxr = AT(ay, e.r_ix);
-    qr = AT(ay, e.r_ix + 1);
-    pir = AT(ay, e.r_ix + 2);
+    clxr = y_r0;
+    qr = y_r1;
+    pir = y_r2;
   }
   if (e.no_phot) {
     if (!e.no_nu) {
@@ -917,9 +936,9 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
     }
     pig = 0;
   } else {
-    clxg = AT(ay, e.g_ix);
-    qg = AT(ay, e.g_ix + 1);
-    if (!e.TightCoupling) pig = AT(ay, e.g_ix + 2);
+    clxg = y_g0;
+    qg = y_g1;
+    if (!e.TightCoupling) pig = y_g2;
   }
   dgrho = dgrho + grhog_t * clxg + grhor_t * clxr;
   dgq = dgq + grhog_t * qg + grhor_t * qr;
@@ -969,12 +988,13 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
     qgdot = 4.0 / 3 * (-vbdot - adotoa * vb + cs2 * k * clxb) / pb43 + denlk(e, 1) * clxg - denlk2(e, 1) * pig;
     AT(ayp, e.g_ix + 1) = qgdot;
     if (!e.TightCoupling) {
-      const double E2 = AT(ay, e.polind + 2);
+      const double E2 = y_e2;
       const double polter = pig / 10 + 9.0 / 15 * E2;
       int ix = e.g_ix + 2;
       if (e.lmaxg > 2) {
-        pigdot = denlk(e, 2) * qg - denlk2(e, 2) * AT(ay, ix + 1) - opacity * (pig - polter) + 8.0 / 15.0 * k * sigma;
+        pigdot = denlk(e, 2) * qg - denlk2(e, 2) * y_g3 - opacity * (pig - polter) + 8.0 / 15.0 * k * sigma;
         AT(ayp, ix) = pigdot;
+#pragma unroll 4
         for (int l = 3; l <= e.lmaxg - 1; l++) {
           ix = ix + 1;
           AT(ayp, ix) = (denlk(e, l) * AT(ay, ix - 1) - denlk2(e, l) * AT(ay, ix + 1)) - opacity * AT(ay, ix);
@@ -987,7 +1007,8 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
       }
       ix = e.polind + 2;
       if (e.lmaxgpol > 2) {
-        AT(ayp, ix) = -opacity * (AT(ay, ix) - polter) - k / 3.0 * AT(ay, ix + 1);
+        AT(ayp, ix) = -opacity * (y_e2 - polter) - k / 3.0 * y_e3;
+#pragma unroll 4
         for (int l = 3; l <= e.lmaxgpol - 1; l++) {
           ix = ix + 1;
           AT(ayp, ix) = -opacity * AT(ay, ix) + (denlk(e, l) * AT(ay, ix - 1) - polfack(e, l) * AT(ay, ix + 1));
@@ -1011,7 +1032,8 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
     } else {
       int ix = e.r_ix + 2;
       if (e.lmaxnr > 2) {
-        AT(ayp, ix) = denlk(e, 2) * qr - denlk2(e, 2) * AT(ay, ix + 1) + 8.0 / 15.0 * k * sigma;
+        AT(ayp, ix) = denlk(e, 2) * qr - denlk2(e, 2) * y_r3 + 8.0 / 15.0 * k * sigma;
+#pragma unroll 4
         for (int l = 3; l <= e.lmaxnr - 1; l++) {
           ix = ix + 1;
           AT(ayp, ix) = (denlk(e, l) * AT(ay, ix - 1) - denlk2(e, l) * AT(ay, ix + 1));
@@ -1054,6 +1076,7 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
           AT(ayp, ind) = -AT(ayp, ind - 2) - 3 * cothxor * AT(ay, ind);
         } else {
           AT(ayp, ind) = v * (denlk(e, 2) * AT(ay, ind - 1) - denlk2(e, 2) * AT(ay, ind + 1)) + k * 8.0 / 15.0 * sigma;
+#pragma unroll 4
           for (int l = 3; l <= e.lmaxnu_tau[nu_i] - 1; l++) {
             ind = ind + 1;
             AT(ayp, ind) = v * (denlk(e, l) * AT(ay, ind - 1) - denlk2(e, l) * AT(ay, ind + 1));
@@ -1069,6 +1092,7 @@ __device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restr
     int ind = e.nu_pert_ix;
     AT(ayp, ind) = +k * a2 * qr - k * AT(ay, ind + 1);
     int ind2 = e.r_ix;
+#pragma unroll 4
     for (int l = 1; l <= e.lmaxnu_pert - 1; l++) {
       ind = ind + 1;
       ind2 = ind2 + 1;
