@@ -290,7 +290,7 @@ __device__ inline void do_switch(Lane& L) {
 }
 
 // Run the lane's control flow until it needs derivs() (returns with L.req_* set) or finishes.
-__device__ __noinline__ void advance(Lane& L) {
+__device__ __forceinline__ void advance(Lane& L) {
   const DevModel& M = *L.M;
   EV& e = L.e;
   const int S = M.SourceNum;

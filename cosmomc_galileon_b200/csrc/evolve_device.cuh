@@ -800,7 +800,7 @@ __device__ inline void Nu_Intvsq(const DevModel& M, const EV& e, const double* y
 // ---------------------------------------------------------------- derivs
 // camb/equations_galileon.f90:2098-2589.  ay / ayp are workspace columns.  Writes e.pig / e.pigdot during
 // tight coupling exactly as the reference does (its value at a switch is the one left by the LAST call).
-__device__ __noinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restrict__ ep, double tau,
+__device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restrict__ ep, double tau,
                                     const double* __restrict__ ay, double* __restrict__ ayp) {
   // __restrict__ on every pointer: the state-vector stores below must not force reloads of the model constants
   // (global) or of the lane's layout descriptor (local) after each store.
