@@ -10,6 +10,7 @@
 // call of derivs() for all of its lanes.  Lanes of a warp therefore share the ~2 kFLOP RHS instruction stream
 // even when they sit in different Runge-Kutta stages, at different step sizes or in different output intervals;
 // only the short bookkeeping between evaluations diverges.
+#include <algorithm>
 #include <cstddef>
 #include <cstdio>
 
@@ -48,6 +49,8 @@ struct Lane {
   EV e;
   const DevModel* M;
   double* ws;  // lane base of the warp workspace
+  double* sm;  // latency mode: lane base of the shared-memory copy of column 9 (and 0 if sm_cols = 2), else nullptr
+  int sm_cols;
   int NV;
   int kidx;
   int phase, stage, j, ind, after_switch;
@@ -73,7 +76,15 @@ struct Lane {
 // shared-memory stride between the Lane records of consecutive threads: sizeof(Lane) rounded up to an odd multiple of 8
 #define GC_LANE_STRIDE ((((sizeof(gc::Lane) + 7) / 8) | 1) * 8)
 
-__device__ __forceinline__ double* col(const Lane& L, int c) { return L.ws + (size_t)c * L.NV * GC_LANES; }
+// Latency mode (few work items, one-warp CTAs): y (column 0) and the stage input w9 (column 9) -- the two columns
+// derivs() reads with dependent loads -- live in shared memory instead (L.sm != nullptr).
+__device__ __forceinline__ double* col(const Lane& L, int c) {
+  if (L.sm) {
+    if (c == 9) return L.sm;
+    if (c == 0 && L.sm_cols > 1) return L.sm + (size_t)L.NV * GC_LANES;
+  }
+  return L.ws + (size_t)c * L.NV * GC_LANES;
+}
 
 // Verner 6(5) stage tableau of camb/subroutines.f90:930-993: w9 = y + temp*(sum_j A[s][j]*w_j), evaluated left to
 // right with the reference's signs so that every partial sum is bit-identical to the Fortran expression.
@@ -535,7 +546,7 @@ __device__ __forceinline__ void advance(Lane& L) {
 __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve_sources_kernel(const DevModel* __restrict__ models, const int2* __restrict__ items,
                                                              int nitems, double* __restrict__ workspace, int NV,
                                                              int* __restrict__ status,
-                                                             unsigned long long* __restrict__ counters) {
+                                                             unsigned long long* __restrict__ counters, int state_in_smem) {
   // The per-lane control state (layout descriptor EV, dverk communication, pending request) lives in SHARED memory:
   // as a local variable it is a 1.2 KB stack frame per thread (470 KB per SM at 12 warps), which thrashes L1 and
   // turned every field access into a long-scoreboard stall.  Stride = odd multiple of 8 B -> conflict-free.
@@ -561,6 +572,10 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
     L.kidx = it.y;
     L.NV = NV;
     L.ws = workspace + (size_t)gwarp * GC_NCOL * NV * GC_LANES + lane;
+    L.sm = state_in_smem ? reinterpret_cast<double*>(gc_smem_raw + (size_t)blockDim.x * GC_LANE_STRIDE) +
+                               (size_t)(threadIdx.x >> 5) * state_in_smem * NV * GC_LANES + lane
+                         : nullptr;
+    L.sm_cols = state_in_smem;
     // DoSourcek, camb/cmbmain.f90:662-689
     L.e.q = M.k[it.y];
     L.e.pig = 0;
@@ -651,18 +666,40 @@ extern "C" void gc_upload_constants() {
 
 extern "C" cudaError_t gc_launch_evolve(const DevModel* models, const int2* items, int nitems, double* workspace, int NV,
                                         int* status, unsigned long long* counters, cudaStream_t stream) {
-  // Few work items (a single model = ~200 items): one warp per CTA so that every warp gets an SM to itself and no
-  // warp waits for another at the lock-step barrier; the run time is then the critical path of one low-k item.
-  const int threads = nitems <= 148 * 64 ? 32 : GC_EVOLVE_THREADS;
-  const size_t smem = (size_t)GC_EVOLVE_THREADS * GC_LANE_STRIDE;  // same carve-out for both shapes
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gc::evolve_sources_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // Few work items (a single model = ~200 items; 128 models = 4 warps per k): one warp per CTA so that every warp
+  // gets (half) an SM to itself and no warp waits for another at the lock-step barrier.  The run time is then the
+  // critical path of one low-k item, so the latency-critical columns move into shared memory.
+  static long lat_items = -1;
+  if (lat_items < 0) {
+    const char* e = getenv("GALCAMB_LATENCY_ITEMS");  // experiment knob: item count up to which latency mode is used
+    lat_items = e ? atol(e) : 160000;  // measured crossover with the lock-step batch mode: ~800 models
+  }
+  const bool latency_mode = nitems <= lat_items;
+  const int threads = latency_mode ? 32 : GC_EVOLVE_THREADS;
+  size_t smem = (size_t)threads * GC_LANE_STRIDE;  // lane records
+  int state_in_smem = 0;
+  if (latency_mode) {
+    // up to 2 warps per SM: both y and w9 in shared memory (82 KB per warp); beyond that only w9 (54 KB, 4 warps/SM)
+    static int cols_env = -2;
+    if (cols_env == -2) {
+      const char* e = getenv("GALCAMB_LATENCY_COLS");
+      cols_env = e ? atoi(e) : -1;
+    }
+    const int cols = cols_env >= 0 ? cols_env : ((nitems + 31) / 32 <= 2 * 148 ? 2 : 1);
+    const size_t extra = (size_t)cols * NV * GC_LANES * sizeof(double);  // column 9 (and 0) of the warp
+    if (cols > 0 && smem + extra <= 113 * 1024) {                        // >= two one-warp CTAs per SM
+      smem += extra;
+      state_in_smem = cols;
+    }
+  }
+  static size_t configured = 0;
+  const size_t want = std::max(smem, (size_t)GC_EVOLVE_THREADS * GC_LANE_STRIDE);
+  if (want > configured) {
+    cudaError_t e = cudaFuncSetAttribute(gc::evolve_sources_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured = want;
   }
   const int blocks = (nitems + threads - 1) / threads;
-  gc::evolve_sources_kernel<<<blocks, threads, (size_t)threads * GC_LANE_STRIDE, stream>>>(models, items, nitems, workspace, NV, status,
-                                                                                          counters);
+  gc::evolve_sources_kernel<<<blocks, threads, smem, stream>>>(models, items, nitems, workspace, NV, status, counters, state_in_smem);
   return cudaGetLastError();
 }
