@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libgalcamb_b200.so")
-SOURCES = ["evolve.cu", "los.cu", "capi.cu", "fp64_peak.cu"]
+SOURCES = ["evolve.cu", "los.cu", "lensing.cu", "capi.cu", "fp64_peak.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FMAD = os.environ.get("GALCAMB_FMAD", "true")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=" + FMAD, "-std=c++17", "-Xcompiler",

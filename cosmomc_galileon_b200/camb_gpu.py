@@ -154,14 +154,18 @@ def load_library():
         L.galcamb_set_bessels_.argtypes = [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_D)]
         L.galcamb_get_bessels_.argtypes = [C.POINTER(_I), C.c_void_p, C.c_void_p, C.c_void_p]
         L.galcamb_set_template_.argtypes = [C.c_void_p, C.POINTER(_I)]
+        L.galcamb_set_lensing_template_.argtypes = [C.c_void_p, C.POINTER(_I)]
+        L.galcamb_get_lensed_cls_.argtypes = [C.POINTER(_I), C.POINTER(_I), C.c_void_p]
         L.galcamb_batch_begin_.argtypes = [C.POINTER(_I)]
         L.galcamb_set_model_.argtypes = [C.POINTER(_I), C.POINTER(CModel)]
         L.galcamb_get_sources_.argtypes = [C.POINTER(_I), C.c_void_p]
         L.galcamb_put_sources_.argtypes = [C.POINTER(_I), C.c_void_p]
         L.galcamb_get_transfers_.argtypes = [C.POINTER(_I), C.c_void_p]
         L.galcamb_get_cls_.argtypes = [C.POINTER(_I), C.c_void_p, C.c_void_p]
+        L.galcamb_put_cls_.argtypes = [C.POINTER(_I), C.c_void_p]
         L.galcamb_get_status_.argtypes = [C.POINTER(_I), C.POINTER(_I)]
         L.galcamb_batch_cls_.argtypes = [C.POINTER(CModel), C.POINTER(_I), C.c_void_p]
+        L.galcamb_batch_lensed_cls_.argtypes = [C.POINTER(CModel), C.POINTER(_I), C.c_void_p, C.POINTER(_I), C.c_void_p]
         L.galcamb_get_timings_.argtypes = [C.c_void_p]
         L.galcamb_get_counters_.argtypes = [C.c_void_p]
         _lib = L
@@ -204,14 +208,19 @@ class GalCamb:
         self._chk(self.L.galcamb_get_bessels_(C.byref(nx), xs.ctypes.data, ajl.ctypes.data, ajlpr.ctypes.data))
         return xs, ajl, ajlpr
 
-    # CheckLoadedHighLTemplate, camb/modules.f90:1222 ; tmpl[type][l-2], type = TT,EE,TE
+    # CheckLoadedHighLTemplate, camb/modules.f90:1222 ; tmpl[type][l-2], type = TT,EE,TE (+ PP for the lensing stage)
     def set_template(self, tmpl):
         if tmpl is None:
             self._chk(self.L.galcamb_set_template_(None, C.byref(_I(0))))
+            self._chk(self.L.galcamb_set_lensing_template_(None, C.byref(_I(0))))
             return
         t = np.ascontiguousarray(tmpl, dtype=np.float64)
-        assert t.shape[0] == 3
-        self._chk(self.L.galcamb_set_template_(t.ctypes.data, C.byref(_I(t.shape[1] + 1))))
+        assert t.shape[0] in (3, 4)
+        t3 = np.ascontiguousarray(t[:3])
+        self._chk(self.L.galcamb_set_template_(t3.ctypes.data, C.byref(_I(t.shape[1] + 1))))
+        if t.shape[0] == 4:
+            pp = np.ascontiguousarray(t[3])
+            self._chk(self.L.galcamb_set_lensing_template_(pp.ctypes.data, C.byref(_I(t.shape[1] + 1))))
 
     def set_models(self, models):
         self.models = list(models)
@@ -230,6 +239,19 @@ class GalCamb:
     # ClTransferToCl, camb/cmbmain.f90:293
     def ClTransferToCl(self):
         self._chk(self.L.galcamb_scalar_cls_())
+
+    # lens_Cls, camb/lensing.f90:78 (after ClTransferToCl on DoLensing models)
+    def lens_Cls(self):
+        rc = self.L.galcamb_lens_cls_()
+        if rc != 8:  # 8 = error_norm_lensing in some slots: their rows are NaN, see status()
+            self._chk(rc)
+
+    def Cl_lensed(self, slot=0):
+        lm = _I(0)
+        self._chk(self.L.galcamb_get_lensed_cls_(C.byref(_I(slot)), C.byref(lm), None))
+        out = np.zeros((4, lm.value - 1))  # [TT,EE,BB,TE][l-2]
+        self._chk(self.L.galcamb_get_lensed_cls_(C.byref(_I(slot)), C.byref(lm), out.ctypes.data))
+        return out
 
     def Src(self, slot=0):
         d = self.models[slot].d
@@ -257,6 +279,10 @@ class GalCamb:
         self._chk(self.L.galcamb_get_cls_(C.byref(_I(slot)), icl.ctypes.data, cl.ctypes.data))
         return icl, cl
 
+    def put_Cls(self, Cl, slot=0):
+        a = np.ascontiguousarray(Cl, dtype=np.float64)
+        self._chk(self.L.galcamb_put_cls_(C.byref(_I(slot)), a.ctypes.data))
+
     # one call for a batch: the public API timed end to end by bench.py
     def batch_cls(self, models, out=None):
         n = len(models)
@@ -270,6 +296,20 @@ class GalCamb:
             self._chk(rc)
         return out
 
+    # the same with the lensing post-step: (Cl[n,3,lmax-1], Cl_lensed[n,4,lmax_lensed-1])
+    def batch_lensed_cls(self, models):
+        n = len(models)
+        arr = (CModel * n)(*[m.cstruct() for m in models])
+        self.models = list(models)
+        lmax = models[0].d["lmax"]
+        out = np.zeros((n, 3, lmax - 1))
+        buf = np.zeros(n * 4 * (lmax - 1))
+        lm = _I(0)
+        rc = self.L.galcamb_batch_lensed_cls_(arr, C.byref(_I(n)), out.ctypes.data, C.byref(lm), buf.ctypes.data)
+        if rc not in (0, 4, 8):
+            self._chk(rc)
+        return out, buf[:n * 4 * (lm.value - 1)].reshape(n, 4, lm.value - 1).copy()
+
     def status(self, slot=0):
         st = _I(0)
         self._chk(self.L.galcamb_get_status_(C.byref(_I(slot)), C.byref(st)))
@@ -278,7 +318,7 @@ class GalCamb:
     def timings(self):
         ms = np.zeros(8)
         self.L.galcamb_get_timings_(ms.ctypes.data)
-        return dict(zip("evolve spline_k los cls h2d d2h bessel total".split(), ms))
+        return dict(zip("evolve spline_k los cls lensing unused bessel total".split(), ms))
 
     def counters(self):
         c = np.zeros(4)

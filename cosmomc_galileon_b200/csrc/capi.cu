@@ -26,6 +26,9 @@ extern "C" cudaError_t gc_launch_los(const DevModel*, int, int, int, int, const 
                                      unsigned long long*, cudaStream_t);
 extern "C" cudaError_t gc_launch_zero_delta(const DevModel*, int, int, cudaStream_t);
 extern "C" cudaError_t gc_launch_cls(const DevModel*, int, const int*, int, int, int, const double*, int, cudaStream_t);
+extern "C" cudaError_t gc_launch_lens_ltab(double4*, double4*, int, cudaStream_t);
+extern "C" cudaError_t gc_launch_lensing(const DevModel*, int, const int*, double, const double4*, const double4*, const double*,
+                                         const double*, int, double4*, const float*, double*, int*, double*, cudaStream_t);
 
 namespace {
 
@@ -68,6 +71,16 @@ struct Ctx {
   // template
   double* d_tmpl = nullptr;
   int lmax_tmpl = 0;
+  double* d_tmpl_pp = nullptr;  // lensing potential column of the template
+  int lmax_tmpl_pp = 0;
+  // lensing work space
+  double4 *d_lens_ta = nullptr, *d_lens_tb = nullptr, *d_lens_cin = nullptr;
+  float* d_lens_apod = nullptr;
+  double *d_lens_partial = nullptr, *d_lensed = nullptr;
+  int* d_lens_status = nullptr;
+  size_t lens_tab_cap = 0, lens_tabb_cap = 0, lens_cin_cap = 0, lens_partial_cap = 0, lensed_cap = 0, lens_status_cap = 0, lens_apod_cap = 0;
+  int lens_tab_lmax = -1, lmax_lensed = 0, lens_nm = 0;
+  std::vector<int> lens_status;
   // neutrino tables (cosmology independent; uploaded from the first model that has them)
   double* d_nu_tab = nullptr;
   bool nu_tab_set = false;
@@ -97,6 +110,17 @@ Ctx g;
       return 100;                                                                                  \
     }                                                                                              \
   } while (0)
+
+template <class T>
+int grow(T*& p, size_t& cap, size_t n) {
+  if (n <= cap) return 0;
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  if (cudaMalloc((void**)&p, n * sizeof(T)) != cudaSuccess) return 1;
+  cap = n;
+  return 0;
+}
 
 int fail(int code, const char* msg) {
   g.err = msg;
@@ -205,7 +229,9 @@ void galcamb_free_(void) {
   }
   g.slots.clear();
   for (void* p : {(void*)g.d_ls, (void*)g.d_xs, (void*)g.d_bess, (void*)g.d_tmpl, (void*)g.d_nu_tab, (void*)g.d_models,
-                  (void*)g.d_items, (void*)g.d_status, (void*)g.d_ws, (void*)g.d_counters})
+                  (void*)g.d_items, (void*)g.d_status, (void*)g.d_ws, (void*)g.d_counters, (void*)g.d_tmpl_pp, (void*)g.d_lens_ta,
+                  (void*)g.d_lens_tb, (void*)g.d_lens_cin, (void*)g.d_lens_apod, (void*)g.d_lens_partial, (void*)g.d_lensed,
+                  (void*)g.d_lens_status})
     if (p) cudaFree(p);
   for (auto& e : g.ev) cudaEventDestroy(e);
   cudaStreamDestroy(g.stream);
@@ -281,6 +307,20 @@ int galcamb_set_template_(const double* tmpl, const int* lmax_tmpl) {
   CK(cudaMalloc((void**)&g.d_tmpl, n * sizeof(double)));
   CK(cudaMemcpy(g.d_tmpl, tmpl, n * sizeof(double), cudaMemcpyHostToDevice));
   g.lmax_tmpl = *lmax_tmpl;
+  return 0;
+}
+
+int galcamb_set_lensing_template_(const double* pp, const int* lmax_tmpl) {
+  if (!g.ready) return fail(100, "not initialised");
+  CK(cudaSetDevice(g.device));
+  if (g.d_tmpl_pp) cudaFree(g.d_tmpl_pp);
+  g.d_tmpl_pp = nullptr;
+  g.lmax_tmpl_pp = 0;
+  if (!pp || *lmax_tmpl < 2) return 0;
+  const size_t n = (size_t)(*lmax_tmpl - 1);
+  CK(cudaMalloc((void**)&g.d_tmpl_pp, n * sizeof(double)));
+  CK(cudaMemcpy(g.d_tmpl_pp, pp, n * sizeof(double), cudaMemcpyHostToDevice));
+  g.lmax_tmpl_pp = *lmax_tmpl;
   return 0;
 }
 
@@ -592,6 +632,94 @@ int galcamb_scalar_cls_(void) {
   return 0;
 }
 
+// lens_Cls / CorrFuncFullSky, camb/lensing.f90:78-215 : geometry of the theta and l sampling on the host, the
+// correlation functions and their transform on the device (csrc/lensing.cu)
+int galcamb_lens_cls_(void) {
+  if (!g.ready) return fail(100, "not initialised");
+  CK(cudaSetDevice(g.device));
+  const int nm = (int)g.slots.size();
+  if (nm < 1) return fail(5, "no models");
+  const int Max_l = g.slots[0].lmax;
+  const double AB = g.slots[0].host.AccuracyBoost;
+  const int HAD = g.slots[0].host.HighAccuracyDefault;
+  for (auto& s : g.slots) {
+    if (!s.set || s.ntype < 6) return fail(5, "lens_cls needs the lensing potential (DoLensing models, 3 sources)");
+    if (s.lmax != Max_l || s.host.AccuracyBoost != AB || s.host.HighAccuracyDefault != HAD)
+      return fail(5, "all models of a lensing batch must share lmax and the accuracy settings");
+  }
+  const double pi = 3.14159265358979323846264338328;
+  int lmax_extrap = Max_l - 100 + 450;
+  if (HAD) lmax_extrap += 300;
+  lmax_extrap = std::min(8000, lmax_extrap);
+  const int lmax = std::max(lmax_extrap, Max_l);
+  if (lmax > Max_l && (!g.d_tmpl || !g.d_tmpl_pp || g.lmax_tmpl < lmax || g.lmax_tmpl_pp != g.lmax_tmpl))
+    return fail(5, "lens_cls needs the high-L template (galcamb_set_template_ + galcamb_set_lensing_template_)");
+  int ix = g.nl - 1;
+  while (g.ls[ix] > Max_l - 100) ix--;  // lensed_convolution_margin, :99-103
+  const int lmax_lensed = g.ls[ix];
+  int npoints = (int)(Max_l * 2 * AB);
+  double dtheta = pi / npoints;
+  if (Max_l > 3500) dtheta = dtheta / (double)1.3f;
+  const int apw = (int)std::lround((double)0.003f / dtheta);
+  npoints = (int)(pi / dtheta);
+  const double range_fac = std::max(1.0, 32 / AB);
+  npoints = (int)(npoints / range_fac);
+  const int interp_fac = std::max(1, std::min((int)std::lround(10 / AB), (int)(range_fac * 2) - 1));
+  const int nblk = (npoints - 1 + 127) / 128;
+  const int geom[7] = {lmax, Max_l, lmax_lensed, npoints, interp_fac, 3 * apw, nblk};
+  if (grow(g.d_lens_ta, g.lens_tab_cap, (size_t)lmax + 5) || grow(g.d_lens_tb, g.lens_tabb_cap, (size_t)lmax + 5))
+    return fail(100, "out of device memory");
+  if (g.lens_tab_lmax != lmax) {
+    CK(gc_launch_lens_ltab(g.d_lens_ta, g.d_lens_tb, lmax, g.stream));
+    g.lens_tab_lmax = lmax;
+  }
+  {  // apodisation window, :467-470 (default-real arithmetic)
+    std::vector<float> w(3 * apw + 1, 1.0f);
+    for (int d = 1; d <= 3 * apw; d++) w[d] = std::exp(-(float)(d * d) / (float)(2 * apw * apw));
+    if (grow(g.d_lens_apod, g.lens_apod_cap, w.size())) return fail(100, "out of device memory");
+    CK(cudaMemcpyAsync(g.d_lens_apod, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+  }
+  if (grow(g.d_lens_cin, g.lens_cin_cap, (size_t)nm * (lmax + 1)) ||
+      grow(g.d_lens_partial, g.lens_partial_cap, (size_t)nm * nblk * 4 * (lmax_lensed + 1)) ||
+      grow(g.d_lensed, g.lensed_cap, (size_t)nm * 4 * (lmax_lensed - 1)) || grow(g.d_lens_status, g.lens_status_cap, (size_t)nm))
+    return fail(100, "out of device memory");
+  if (int rc = upload_models()) return rc;
+  CK(cudaEventRecord(g.ev[7], g.stream));
+  CK(gc_launch_lensing(g.d_models, nm, geom, dtheta, g.d_lens_ta, g.d_lens_tb, g.d_tmpl, g.d_tmpl_pp, g.lmax_tmpl, g.d_lens_cin,
+                       g.d_lens_apod, g.d_lens_partial, g.d_lens_status, g.d_lensed, g.stream));
+  CK(cudaEventRecord(g.ev[8], g.stream));
+  g.lens_status.assign(nm, 0);
+  CK(cudaMemcpyAsync(g.lens_status.data(), g.d_lens_status, nm * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, g.ev[7], g.ev[8]);
+  g.ms[4] = ms;
+  g.lmax_lensed = lmax_lensed;
+  g.lens_nm = nm;
+  int rc = 0;
+  for (int i = 0; i < nm; i++)
+    if (g.lens_status[i] && !g.slots[i].status) {
+      g.slots[i].status = 8;  // error_norm_lensing
+      rc = 8;
+    }
+  if (rc) g.err = "You need to normalize realistically to use lensing (camb/lensing.f90:230-235)";
+  return rc;
+}
+
+int galcamb_get_lensed_cls_(const int* slot, int* lmax_lensed, double* Cl_lensed) {
+  if (*slot < 0 || *slot >= g.lens_nm || !g.d_lensed) return fail(5, "bad slot / lens_cls not run");
+  *lmax_lensed = g.lmax_lensed;
+  if (Cl_lensed) {
+    const size_t per = (size_t)4 * (g.lmax_lensed - 1);
+    CK(cudaMemcpyAsync(Cl_lensed, g.d_lensed + per * *slot, per * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    if (g.slots[*slot].status)
+      for (size_t j = 0; j < per; j++) Cl_lensed[j] = std::nan("");
+  }
+  return 0;
+}
+
 int galcamb_get_sources_(const int* slot, double* Src) {
   if (*slot < 0 || *slot >= (int)g.slots.size() || !g.slots[*slot].set) return fail(5, "bad slot");
   const DevModel& D = g.slots[*slot].host;
@@ -621,6 +749,14 @@ int galcamb_get_cls_(const int* slot, double* iCl, double* Cl) {
   const Slot& s = g.slots[*slot];
   if (iCl) CK(cudaMemcpyAsync(iCl, s.host.iCl, (size_t)s.ntype * g.nl * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
   if (Cl) CK(cudaMemcpyAsync(Cl, s.host.Cl, (size_t)s.ntype * (s.lmax - 1) * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int galcamb_put_cls_(const int* slot, const double* Cl) {
+  if (*slot < 0 || *slot >= (int)g.slots.size() || !g.slots[*slot].set) return fail(5, "bad slot");
+  const Slot& s = g.slots[*slot];
+  CK(cudaMemcpyAsync(s.host.Cl, Cl, (size_t)s.ntype * (s.lmax - 1) * sizeof(double), cudaMemcpyHostToDevice, g.stream));
   CK(cudaStreamSynchronize(g.stream));
   return 0;
 }
@@ -674,9 +810,34 @@ int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* 
   return rc_ev;
 }
 
+// galcamb_batch_cls_ followed by the lensing post-step: what CAMB_GetResults hands CosmoMC when DoLensing = T
+// (Cl_lensed, camb/camb.f90:167-171 -> camb/lensing.f90:78).  Cl_out may be NULL.
+int galcamb_batch_lensed_cls_(const galcamb_model* models, const int* nmodels, double* Cl_out, int* lmax_lensed,
+                              double* Cl_lensed_out) {
+  if (!g.ready) return fail(100, "not initialised");
+  const int lmax = models[0].lmax;
+  std::vector<double> tmp;
+  if (!Cl_out) {
+    tmp.resize((size_t)3 * (lmax - 1) * *nmodels);
+    Cl_out = tmp.data();
+  }
+  const int rc_ev = galcamb_batch_cls_(models, nmodels, Cl_out);
+  if (rc_ev != 0 && rc_ev != 4) return rc_ev;
+  const int rc_l = galcamb_lens_cls_();
+  if (rc_l != 0 && rc_l != 8) return rc_l;
+  *lmax_lensed = g.lmax_lensed;
+  const size_t per = (size_t)4 * (g.lmax_lensed - 1);
+  CK(cudaMemcpyAsync(Cl_lensed_out, g.d_lensed, per * *nmodels * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  for (int i = 0; i < *nmodels; i++)
+    if (g.slots[i].status)
+      for (size_t j = 0; j < per; j++) Cl_lensed_out[per * i + j] = std::nan("");
+  return rc_ev ? rc_ev : rc_l;
+}
+
 int galcamb_get_timings_(double* ms) {
   for (int i = 0; i < 8; i++) ms[i] = g.ms[i];
-  ms[7] = g.ms[0] + g.ms[1] + g.ms[2] + g.ms[3];
+  ms[7] = g.ms[0] + g.ms[1] + g.ms[2] + g.ms[3];  // the unlensed path; ms[4] = lensing
   return 0;
 }
 

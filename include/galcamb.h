@@ -95,6 +95,9 @@ int galcamb_set_bessels_(const int* ls, const int* nl, const int* kmaxfile, cons
 /* fiducial template highL_CL_template(lmin:lmax_tmpl, 1:3) = TT,EE,TE (camb/modules.f90:1222-1245), laid out
  * [type][l-2]; pass lmax_tmpl = 0 for use_spline_template = F. */
 int galcamb_set_template_(const double* tmpl, const int* lmax_tmpl);
+/* 4th column of the same template file, the lensing potential [l(l+1)]^2 C_l^phiphi/2pi (camb/modules.f90:1236-1240),
+ * [l-2]; only the lensing stage reads it (extrapolation beyond Max_l, camb/lensing.f90:237-253). */
+int galcamb_set_lensing_template_(const double* pp, const int* lmax_tmpl);
 
 /* --- batch of models ------------------------------------------------------------------------------- */
 int galcamb_batch_begin_(const int* nmodels);
@@ -113,14 +116,27 @@ int galcamb_get_sources_(const int* slot, double* Src);
 int galcamb_put_sources_(const int* slot, const double* Src); /* feed stage 3 with host-computed sources */
 int galcamb_get_transfers_(const int* slot, double* Delta_p_l_k);
 int galcamb_get_cls_(const int* slot, double* iCl, double* Cl); /* either pointer may be NULL */
+int galcamb_put_cls_(const int* slot, const double* Cl);         /* feed stage 5 with host-computed Cl_scalar */
 int galcamb_get_status_(const int* slot, int* status);           /* per-slot CAMB error id */
+
+/* stage 5 (post-step of the path): lens_Cls -> CorrFuncFullSky -> CorrFuncFullSkyImpl, camb/lensing.f90:78-528
+ * (lensing_method = 1, AccurateBB = F, no tensors), on the device-resident Cl_scalar of every slot of the batch.
+ * The models must carry the lensing potential (DoLensing: 3 sources) and share lmax and accuracy settings.
+ * Returns 8 (error_norm_lensing, camb/constants.f90:80) if a slot fails the normalisation check (:230-235).
+ *   Cl_lensed(lmin:lmax_lensed, 1:4) = TT, EE, BB, TE laid out [type][l-2] */
+int galcamb_lens_cls_(void);
+int galcamb_get_lensed_cls_(const int* slot, int* lmax_lensed, double* Cl_lensed /* may be NULL */);
 
 /* one call for a whole batch: set models, run stages 1-4, return Cl(lmin:lmax,3) per model contiguous */
 int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* Cl_out);
+/* the same followed by stage 5: additionally returns Cl_lensed(lmin:lmax_lensed,4) per model contiguous (the caller
+ * sizes it for lmax_lensed <= lmax - 100); Cl_out may be NULL.  Failed slots are NaN rows (status 4 or 8). */
+int galcamb_batch_lensed_cls_(const galcamb_model* models, const int* nmodels, double* Cl_out, int* lmax_lensed,
+                              double* Cl_lensed_out);
 
 /* measurement hooks (bench.py): last stage durations in ms (CUDA events on the library stream) and the
  * algorithmic work counters of SURVEY.md section 8(d). */
-int galcamb_get_timings_(double* ms /*[8]: evolve, spline_k, los, cls, h2d, d2h, bessel, total*/);
+int galcamb_get_timings_(double* ms /*[8]: evolve, spline_k, los, cls, lensing, -, bessel, total of 0..3*/);
 int galcamb_get_counters_(double* c /*[4]: n_derivs, sum_n, n_out, n_iter*/);
 int galcamb_sync_(void);
 /* FP64 FMA micro-benchmark (roofline denominator): out[0] = device peak TFLOP/s, out[1], out[2] = one warp per SM with

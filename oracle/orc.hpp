@@ -258,6 +258,8 @@ struct Model {
   std::vector<double> Delta_p_l_k; // (S, nl, nq) column-major
   std::vector<double> iCl_scalar;  // (nl, C_last)
   std::vector<double> Cl_scalar;   // (lmin..Max_l, C_last): idx = (l-lmin) + (Max_l-lmin+1)*(type-1)
+  std::vector<double> Cl_lensed;   // (lmin..lmax_lensed, 4) TT,EE,BB,TE : idx = (l-lmin) + nLl*(type-1)
+  int lmax_lensed = 0;
   std::vector<double> highL_template;  // (lmin..8000, 4) TT,EE,TE,PP ; idx=(l-lmin)+7999*(t-1)
   int error_flag = 0;
   std::string error_msg;
@@ -328,5 +330,6 @@ double ScalarPower(const Model& M, double k);
 int run_all(Model& M);                    // CAMB_GetResults for the scalar flat path
 int run_model(Model& M, double* stage_times, bool reuse_bessels);
 int load_highL_template(Model& M, const char* path);
+int lens_Cls(Model& M);                   // camb/lensing.f90:78-528 (curved-sky correlation function method)
 
 }  // namespace orc

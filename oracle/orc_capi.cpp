@@ -121,6 +121,8 @@ int orc_stage_cls(void* h) {
   return 0;
 }
 
+int orc_stage_lensing(void* h) { return lens_Cls(*(Model*)h); }
+
 const char* orc_error(void* h) { return ((Model*)h)->error_msg.c_str(); }
 
 double orc_get(void* h, const char* name) {
@@ -132,6 +134,7 @@ double orc_get(void* h, const char* name) {
   G(kmaxfile) G(epsw) G(Max_eta_k) G(Nu_mass_eigenstates) G(Num_Nu_massive) G(reion_redshift) G(reion_tau_start)
   G(reion_tau_complete) G(error_flag) G(maximum_l) G(scale) G(omegak)
 #undef G
+  if (n == "lmax_lensed") return M.lmax_lensed;
   if (n == "nk") return M.Evolve_q.npoints;
   if (n == "nt") return M.TimeSteps.npoints;
   if (n == "nq") return M.q_int.npoints;
@@ -189,6 +192,7 @@ long orc_get_array(void* h, const char* name, double* out, long cap) {
   else if (n == "iCl") zero(M.iCl_scalar);
   else if (n == "Cl") zero(M.Cl_scalar);
   else if (n == "template") zero(M.highL_template);
+  else if (n == "Cl_lensed") zero(M.Cl_lensed);
   else if (n == "cs2") one(M.th.cs2);
   else if (n == "dcs2") one(M.th.dcs2);
   else if (n == "dotmu") one(M.th.dotmu);
@@ -257,7 +261,10 @@ long orc_put_array(void* h, const char* name, const double* in, long len) {
   if (n == "Src") v = &M.Src;
   else if (n == "ddSrc") v = &M.ddSrc;
   else if (n == "Delta_p_l_k") v = &M.Delta_p_l_k;
-  else return -1;
+  else if (n == "Cl") {  // feed the lensing stage alone (tests): (lmin..Max_l, C_last)
+    v = &M.Cl_scalar;
+    if (len == (long)(M.P.Max_l - lmin + 1) * M.C_last) v->resize(len);
+  } else return -1;
   if ((long)v->size() != len) return -2;
   for (long i = 0; i < len; i++) (*v)[i] = in[i];
   return len;

@@ -32,7 +32,7 @@ def lib():
         L.orc_set_physical.argtypes = [C.c_void_p] + [C.c_double] * 4
         L.orc_load_template.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_run.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
-        for s in ("background", "initvars", "sources", "spline_k", "bessels", "los", "cls"):
+        for s in ("background", "initvars", "sources", "spline_k", "bessels", "los", "cls", "lensing"):
             getattr(L, "orc_stage_" + s).argtypes = [C.c_void_p]
         L.orc_alloc_sources.argtypes = [C.c_void_p]
         L.orc_source_k.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
@@ -143,6 +143,10 @@ class Oracle:
     def Cl(self):
         nL = self.geti("maximum_l") - 1
         return self.arr("Cl").reshape(self.geti("C_last"), nL)  # [type][l-2], dimensionless l(l+1)C_l/2pi
+
+    def Cl_lensed(self):
+        nLl = self.geti("lmax_lensed") - 1
+        return self.arr("Cl_lensed").reshape(4, nLl)  # [TT,EE,BB,TE][l-2]
 
     def iCl(self):
         return self.arr("iCl").reshape(self.geti("C_last"), self.geti("nl"))

@@ -25,7 +25,7 @@ def relmax(a, b):
 def gpu():
     from cosmomc_galileon_b200 import GalCamb
     g = GalCamb(0)
-    tmpl = np.fromfile(os.path.join(GOLD, "highL_template.f64")).reshape(7999, 4)[:, :3].T.copy()
+    tmpl = np.fromfile(os.path.join(GOLD, "highL_template.f64")).reshape(7999, 4).T.copy()  # TT, EE, TE, PP
     g.set_template(tmpl)
     yield g
 
@@ -84,6 +84,65 @@ def test_three_source_variants_against_oracle(gpu, kw, lmax):
     assert np.max(np.abs(cl[:4] / o.Cl()[:4] - 1)) < TOL_CL  # TT, EE, TE, phi-phi
     for t_ in (4, 5):  # phi-T and phi-E cross spectra change sign: compare on the max-norm
         assert relmax(cl[t_], o.Cl()[t_]) < TOL_CL
+    # stage 5: lensed spectra from the device-resident C_l (camb/lensing.f90:107-528)
+    o.stage("lensing")
+    gpu.lens_Cls()
+    check_lensed(gpu.Cl_lensed(), o.Cl_lensed(), TOL_CL)
+    assert gpu.Cl_lensed().shape[1] == o.geti("lmax_lensed") - 1
+    # and through the one-call batch entry CosmoMC would use with DoLensing = T
+    tau = t.d["tau"].copy()
+    tau[40] = tau[39]  # a point dverk rejects (see test_failed_point_does_not_sink_the_batch)
+    cl_b, lensed_b = gpu.batch_lensed_cls([t, t.copy(tau=tau)])
+    check_lensed(lensed_b[0], o.Cl_lensed(), TOL_CL)
+    assert np.max(np.abs(cl_b[0, :2] / o.Cl()[:2] - 1)) < TOL_CL
+    assert gpu.status(0) == 0 and gpu.status(1) == 4 and np.all(np.isnan(lensed_b[1]))
+
+
+def check_lensed(L, Lo, tol):
+    assert L.shape == Lo.shape
+    for t_ in (0, 1, 2):  # TT, EE, BB are positive
+        assert np.max(np.abs(L[t_] / Lo[t_] - 1)) < tol, t_
+    # TE changes sign: max-norm over a sliding window of 50 multipoles (the spectrum falls by 1e4 over the range)
+    n = L.shape[1] // 50 * 50
+    a, b = L[3, :n].reshape(-1, 50), Lo[3, :n].reshape(-1, 50)
+    assert np.max(np.max(np.abs(a - b), axis=1) / np.max(np.abs(b), axis=1)) < tol
+
+
+def test_lensing_stage_alone_high_l(gpu):
+    """BASELINE configs[2] geometry for the lensing stage (lmax 5000, AccuracyBoost 2: 1625 angles in 13 CTAs per
+    model, the Max_l > 3500 step refinement, template extrapolation to l = 5650) without paying for the AccuracyBoost=2
+    ODE: both sides get the C_l of an AccuracyBoost=1 oracle run.  Then the properties the transform has at any size:
+    linearity in the unlensed CMB spectra at fixed potential, and a realistic-normalisation failure stays in its slot."""
+    from oracle_py import Oracle
+    from tables_from_oracle import tables_from_oracle
+    P = dict(GAL)
+    P.update(DoLensing=1)
+    oA = Oracle(lmax=5000, **P)
+    oA.run()
+    Cl = oA.Cl()
+    P2 = dict(P)
+    P2.update(AccuracyBoost=2)
+    oB = Oracle(lmax=5000, **P2)
+    oB.stage("background", "initvars")
+    oB.put("Cl", Cl)
+    oB.stage("lensing")
+    Lo = oB.Cl_lensed()
+    assert oB.geti("lmax_lensed") == 4900
+    t = tables_from_oracle(oB, P2, lmax=5000)
+    gpu.InitSpherBessels(t.ls, t.d["kmaxfile"], t.d["AccuracyBoost"])
+    Cl2 = Cl.copy()
+    Cl2[:3] *= 0.6
+    Cl3 = Cl.copy()
+    Cl3[3] *= 1e3  # lensing potential far too large: error_norm_lensing (camb/lensing.f90:230-235)
+    gpu.set_models([t, t.copy(), t.copy()])
+    for i, c in enumerate((Cl, Cl2, Cl3)):
+        gpu.put_Cls(c, i)
+    gpu.lens_Cls()
+    L = gpu.Cl_lensed(0)
+    check_lensed(L, Lo, TOL_CL)
+    np.testing.assert_allclose(gpu.Cl_lensed(1), 0.6 * L, rtol=1e-11)
+    assert gpu.status(0) == 0 and gpu.status(1) == 0 and gpu.status(2) == 8
+    assert np.all(np.isnan(gpu.Cl_lensed(2)))
 
 
 def test_bessel_tables_against_oracle(gpu):
