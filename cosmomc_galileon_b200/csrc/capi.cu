@@ -342,6 +342,7 @@ static int pack_model(int islot, const galcamb_model* m) {
   if (g.nl == 0) return fail(5, "galcamb_set_bessels_ must be called first");
   if (m->Nu_mass_eigenstates > GC_MAX_NU || m->nqmax > GC_MAX_NQ) return fail(5, "too many neutrino eigenstates / q nodes");
   if (m->n_tau_regions > GC_MAX_REGIONS) return fail(5, "too many TimeSteps regions");
+  if (m->nk < 2 || m->nq < 1 || m->nt < 2 || m->lmax < 2) return fail(5, "empty k, q or time grid in galcamb_model");
   Slot& s = g.slots[*slot];
   DevModel& D = s.host;
   D = DevModel{};
@@ -551,7 +552,7 @@ int galcamb_evolve_sources_(void) {
     g.items_cap = nitems;
   }
   const size_t nwarps = (nitems + 31) / 32;
-  const size_t ws_need = nwarps * 10 * (size_t)NV * 32;
+  const size_t ws_need = nwarps * 12 * (size_t)NV * 32;  // GC_NCOL columns (csrc/evolve_device.cuh)
   if (grow(&g.d_ws, &g.ws_cap, ws_need)) return fail(100, "cudaMalloc workspace");
   CK(cudaMemcpyAsync(g.d_items, g.items.data(), nitems * sizeof(int2), cudaMemcpyHostToDevice, g.stream));
   CK(cudaMemsetAsync(g.d_counters, 0, 8 * sizeof(unsigned long long), g.stream));

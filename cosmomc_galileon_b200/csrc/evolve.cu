@@ -34,6 +34,7 @@ enum Phase : int {
   PH_DV_LOOP,
   PH_DV_K1,
   PH_DV_STAGE,
+  PH_DV_FINAL,
   PH_OUT_REQ,
   PH_OUT_DONE,
   PH_DONE
@@ -54,16 +55,28 @@ struct Lane {
   int NV;
   int kidx;
   int phase, stage, j, ind, after_switch;
-  bool evaluated;
   double tau, tauend, target;
   // dverk communication (c(13), c(14), c(17), c(18), c(19), c(20), c(21), c(23))
   double hmin, hmag, xtrial, htrial, est, c20, c21, nfail;
   // pending RHS request
   double req_tau;
   int req_in, req_out;
+  bool want_derivs;
+  // pending stage combination (row of the tableau, -1 = none) and its scale h/D; results of a final row
+  int crow;
+  double errn, ynorm_new;
+  // max|y_i| of the accepted state (dverk's c(12) input), kept up to date by the final row
+  double ynorm;
+  bool ynorm_valid;
+  int ysel;  // which physical column (0 or 9) currently holds y; the other one is the stage input w9
+  // deferred output (see flush_output): the sources of output time out_j are formed later, together with the other
+  // lanes' pending outputs, from y (stashed in column 10 by the next combine()), y' (column 11) and these scalars
+  bool out_pending, out_stashed, flush_now;
+  int out_j;
+  double out_pig, out_pigdot;
   int status;
   // work counters
-  unsigned long long n_derivs, sum_n, n_out;
+  unsigned n_derivs, sum_n, n_out;  // per lane: < 1e5 evaluations of < 200 equations
 #if GC_HOT_IN_SMEM
   // private copy of the model's hot block (the prefix of DevModel that derivs() and its helpers read): in batch mode
   // the 32 lanes of a warp belong to 32 different models, so reading the constants from the DevModel array costs 32
@@ -75,99 +88,152 @@ struct Lane {
 // element i of column c of this lane: ws[(c*NV + i-1)*32]  (ws already points at the lane's slot)
 // shared-memory stride between the Lane records of consecutive threads: sizeof(Lane) rounded up to an odd multiple of 8
 #define GC_LANE_STRIDE ((((sizeof(gc::Lane) + 7) / 8) | 1) * 8)
+// two 128-thread CTAs per SM need 2 x (128 x stride + 1 KB) <= 228 KB
+static_assert(GC_LANE_STRIDE <= 904, "Lane record too large for two CTAs per SM");
 
 // Latency mode (few work items, one-warp CTAs): y (column 0) and the stage input w9 (column 9) -- the two columns
 // derivs() reads with dependent loads -- live in shared memory instead (L.sm != nullptr).
+// logical column c of the lane (0 = y, 1..8 = k1..k8, 9 = stage input / trial solution).  y and w9 trade places
+// when a trial step is accepted (L.ysel), so accepting a step costs no copy.
+__device__ __forceinline__ int phys_col(const Lane& L, int c) {
+  if (c == 0) return L.ysel ? 9 : 0;
+  if (c == 9) return L.ysel ? 0 : 9;
+  return c;
+}
 __device__ __forceinline__ double* col(const Lane& L, int c) {
+  const int p = phys_col(L, c);
   if (L.sm) {
-    if (c == 9) return L.sm;
-    if (c == 0 && L.sm_cols > 1) return L.sm + (size_t)L.NV * GC_LANES;
+    if (p == 9) return L.sm;
+    if (p == 0 && L.sm_cols > 1) return L.sm + (size_t)L.NV * GC_LANES;
   }
-  return L.ws + (size_t)c * L.NV * GC_LANES;
+  return L.ws + (size_t)p * L.NV * GC_LANES;
 }
 
-// Verner 6(5) stage tableau of camb/subroutines.f90:930-993: w9 = y + temp*(sum_j A[s][j]*w_j), evaluated left to
-// right with the reference's signs so that every partial sum is bit-identical to the Fortran expression.
-__constant__ double c_A[7][7] = {
-    {233028180000.0, 0, 0, 0, 0, 0, 0},
-    {74569017600.0, 298276070400.0, 0, 0, 0, 0, 0},
-    {1165140900000.0, -3728450880000.0, 3495422700000.0, 0, 0, 0, 0},
-    {-3604654659375.0, 12816549900000.0, -9284716546875.0, 1237962206250.0, 0, 0, 0},
-    {3355605792000.0, -11185352640000.0, 9172628850000.0, -427218330000.0, 482505408000.0, 0, 0},
-    {-770204740536.0, 2311639545600.0, -1322092233000.0, -453006781920.0, 326875481856.0, 0, 0},
-    {2845924389000.0, -9754668000000.0, 7897110375000.0, -192082660000.0, 400298976000.0, 0, 201586000000.0}};
-__constant__ int c_Aused[7][7] = {{1, 0, 0, 0, 0, 0, 0}, {1, 1, 0, 0, 0, 0, 0}, {1, 1, 1, 0, 0, 0, 0}, {1, 1, 1, 1, 0, 0, 0},
-                                  {1, 1, 1, 1, 1, 0, 0}, {1, 1, 1, 1, 1, 0, 0}, {1, 1, 1, 1, 1, 0, 1}};
+// Verner 6(5) tableau of camb/subroutines.f90:930-1019 as rows over the derivative columns w1..w8:
+//   rows 0..6  stage inputs   w9 = y + temp*(sum_j c_row[r][j]*w_j)            (:930-993)
+//   row  7     trial solution w9 = y + temp*(sum_j c_row[7][j]*w_j)  and the error vector
+//              w2 = (sum_j c_err[j]*w_j)/1398169080000                         (:995-1019)
+// every sum runs left to right over ascending j with the reference's signs, so each partial sum equals the Fortran
+// expression's.  c_rowmask[r] = the columns row r reads.
+__constant__ double c_row[8][8] = {
+    {233028180000.0, 0, 0, 0, 0, 0, 0, 0},
+    {74569017600.0, 298276070400.0, 0, 0, 0, 0, 0, 0},
+    {1165140900000.0, -3728450880000.0, 3495422700000.0, 0, 0, 0, 0, 0},
+    {-3604654659375.0, 12816549900000.0, -9284716546875.0, 1237962206250.0, 0, 0, 0, 0},
+    {3355605792000.0, -11185352640000.0, 9172628850000.0, -427218330000.0, 482505408000.0, 0, 0, 0},
+    {-770204740536.0, 2311639545600.0, -1322092233000.0, -453006781920.0, 326875481856.0, 0, 0, 0},
+    {2845924389000.0, -9754668000000.0, 7897110375000.0, -192082660000.0, 400298976000.0, 0, 201586000000.0, 0},
+    {104862681000.0, 0, 545186250000.0, 446637345000.0, 188806464000.0, 0, 15076875000.0, 97599465000.0}};
+__constant__ double c_err[8] = {8738556750.0,  0, 9735468750.0, -9709507500.0, 8582112000.0, 95329710000.0,
+                                -15076875000.0, -97599465000.0};
+__constant__ unsigned c_rowmask[8] = {0x01, 0x03, 0x07, 0x0f, 0x1f, 0x1f, 0x5f, 0xfd};
 
-
-// w9 = y + temp * sum_j A[row][j] * w_(j+1), left to right as in camb/subroutines.f90:930-993
-template <int NC>
-__device__ __forceinline__ void stage_input_t(const double* __restrict__ y, double* __restrict__ w9, const double* const* kc,
-                                              const double* cf, int n, double temp) {
-  int i = 1;
-  for (; i + 3 <= n; i += 4) {
-    double yv[4], kv[NC][4];
+// ONE stage-combination routine for every row of the tableau, executed by the whole warp together: each lane brings
+// its own row (L.crow), length and scale, so lanes that sit in different Runge-Kutta stages -- the normal state of
+// a warp whose 32 lanes integrate 32 different cosmologies -- share one pass over the columns instead of running
+// one specialised loop per stage present in the warp one after the other.  4 elements x 4 columns of independent
+// loads are in flight per batch (the columns live in L2/HBM).
+__device__ __forceinline__ void combine(Lane& L) {
+  const bool on = L.crow >= 0;
+  const int r = on ? L.crow : 0;
+  const int n = on ? L.e.neq : 0;
+  const unsigned cmask = on ? c_rowmask[r] : 0u;
+  const int nmax = __reduce_max_sync(0xffffffffu, n);
+  const unsigned umask = __reduce_or_sync(0xffffffffu, cmask);
+  const bool fin = on && r == 7;
+  const bool any_fin = __any_sync(0xffffffffu, fin);
+  double cf[8], ce[8];
 #pragma unroll
-    for (int u = 0; u < 4; u++) yv[u] = AT(y, i + u);
+  for (int j = 0; j < 8; j++) {
+    cf[j] = c_row[r][j];
+    ce[j] = fin ? c_err[j] : 0.0;
+  }
+  const double* __restrict__ y = col(L, 0);
+  double* __restrict__ w9 = col(L, 9);
+  const double* kc[8];
 #pragma unroll
-    for (int c = 0; c < NC; c++)
-#pragma unroll
-      for (int u = 0; u < 4; u++) kv[c][u] = AT(kc[c], i + u);
+  for (int j = 0; j < 8; j++) kc[j] = L.ws + (size_t)(j + 1) * L.NV * GC_LANES;
+  const double temp = L.htrial / 1398169080000.0;
+  double errn = 0.0, ynew = 0.0;
+  // a lane whose last output is still pending keeps a copy of that y (this is the first pass over y since then)
+  const bool stash = on && L.out_pending && !L.out_stashed;
+  double* __restrict__ ys = L.ws + (size_t)10 * L.NV * GC_LANES;
+  for (int i = 1; i <= nmax; i += 4) {
+    // all loads of the batch first (up to 4 + 8 x 4 independent loads in flight), then the arithmetic, then the stores
+    double yv[4], kv[8][4];
+    bool p[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      double acc = kv[0][u] * cf[0];
+      p[u] = i + u <= n;
+      yv[u] = p[u] ? AT(y, i + u) : 0.0;
+    }
 #pragma unroll
-      for (int c = 1; c < NC; c++) acc = acc + kv[c][u] * cf[c];
-      AT(w9, i + u) = yv[u] + temp * acc;
+    for (int c = 0; c < 8; c++) {
+      if (umask & (1u << c)) {
+        const bool mine = (cmask >> c) & 1u;
+#pragma unroll
+        for (int u = 0; u < 4; u++) kv[c][u] = (mine && p[u]) ? AT(kc[c], i + u) : 0.0;
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; u++) kv[c][u] = 0.0;
+      }
+    }
+    double a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      if (umask & (1u << c)) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) a1[u] = a1[u] + kv[c][u] * cf[c];
+      }
+    }
+    if (any_fin) {
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) a2[u] = a2[u] + kv[c][u] * ce[c];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (p[u]) {
+        // row 0 keeps the reference's association y + (temp*w1)*c  (camb/subroutines.f90:930)
+        const double v = (r == 0) ? yv[u] + temp * kv[0][u] * 233028180000.0 : yv[u] + temp * a1[u];
+        AT(w9, i + u) = v;
+        if (stash) AT(ys, i + u) = yv[u];
+        if (fin) {
+          const double w2 = a2[u] / 1398169080000.0;
+          errn = fmax(errn, fabs(w2) / fmax(1.0, fabs(yv[u])));
+          ynew = fmax(ynew, fabs(v));
+        }
+      }
     }
   }
-  for (; i <= n; i++) {
-    double acc = AT(kc[0], i) * cf[0];
-#pragma unroll
-    for (int c = 1; c < NC; c++) acc = acc + AT(kc[c], i) * cf[c];
-    AT(w9, i) = AT(y, i) + temp * acc;
+  if (fin) {
+    L.errn = errn;
+    L.ynorm_new = ynew;
   }
+  if (stash) L.out_stashed = true;
+  L.crow = -1;
 }
 
-__device__ __forceinline__ void stage_input(Lane& L, int row, int n, double temp) {
-  const double* y = col(L, 0);
-  double* w9 = col(L, 9);
-  const double* kc[6];
-  double cf[6];
-  int nc = 0;
-#pragma unroll
-  for (int jj = 0; jj < 7; jj++)
-    if (c_Aused[row][jj]) {
-      kc[nc] = col(L, jj + 1);
-      cf[nc] = c_A[row][jj];
-      nc++;
-    }
-  switch (nc) {
-    case 2: stage_input_t<2>(y, w9, kc, cf, n, temp); break;
-    case 3: stage_input_t<3>(y, w9, kc, cf, n, temp); break;
-    case 4: stage_input_t<4>(y, w9, kc, cf, n, temp); break;
-    case 5: stage_input_t<5>(y, w9, kc, cf, n, temp); break;
-    default: stage_input_t<6>(y, w9, kc, cf, n, temp); break;
-  }
-}
-
-// The stage derivatives w2..w8 and the stage input w9 are dead once a trial step has been accepted or rejected;
-// they will be rewritten before they are read again.  Dropping their (dirty) lines from L2 without write-back keeps
-// the dead 70 % of the workspace from being streamed to HBM and from competing with live lines for L2 capacity.
-// One 256-byte row per element = two 128-byte lines; lanes 0 and 16 issue the discard for "their" line.
-#ifndef GC_DISCARD_DEAD
-#define GC_DISCARD_DEAD 1
-#endif
-// A line holds the same element of 16 lanes, so it may only be dropped when all 16 lanes of that half-warp are at
-// this very point of their trial step together (true in lock-step batches; otherwise the lines are simply kept).
-__device__ __forceinline__ void discard_rows(const double* colp, int n) {
-#if GC_DISCARD_DEAD
-  const unsigned grp = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
-  const bool together = (__activemask() & grp) == grp;
-  if (together && (threadIdx.x & 15) == 0) {
-    for (int i = 1; i <= n; i++) asm volatile("discard.global.L2 [%0], 128;" ::"l"(&AT(colp, i)) : "memory");
-  }
-#endif
+// Deferred output_sources(): called from the main loop when ANY lane of the warp must have its pending output out
+// of the way (it reached its next output time, a switch or the end); every lane with a pending output joins, so a
+// warp whose lanes reach their output times in different iterations still runs the ~2 kFLOP source evaluation about
+// once per output interval instead of once per lane.  Nothing the evaluation reads changes in between: y is
+// stashed, y' sits in its own column, the layout descriptor only changes at switches (which flush first), and the
+// tight-coupling scalars derivs() leaves in EV (camb/equations_galileon.f90:2407,2417) are saved and put back.
+__device__ __forceinline__ void flush_output(Lane& L) {
+  const DevModel& M = *L.M;
+  const int S = M.SourceNum;
+  const double pig = L.e.pig, pigdot = L.e.pigdot;
+  L.e.pig = L.out_pig;
+  L.e.pigdot = L.out_pigdot;
+  double src[3] = {0, 0, 0};
+  const double* y = L.out_stashed ? L.ws + (size_t)10 * L.NV * GC_LANES : col(L, 0);
+  output_sources(L.M, &L.e, y, col(L, 11), M.ts + (size_t)(L.out_j - 1) * 8, M.ts[(size_t)(L.out_j - 1) * 8], src);
+  for (int s = 0; s < S; s++) M.Src[((size_t)(L.out_j - 1) * S + s) * M.nk + L.kidx] = src[s];
+  L.e.pig = pig;
+  L.e.pigdot = pigdot;
+  L.out_pending = false;
 }
 
 struct Switches {
@@ -309,6 +375,10 @@ __device__ __forceinline__ void advance(Lane& L) {
   for (;;) {
     switch (L.phase) {
       case PH_NEXT_OUTPUT: {
+        if (L.j + 1 > M.nt && L.out_pending) {  // the last output must be out before the lane retires
+          L.flush_now = true;
+          return;
+        }
         L.j++;
         if (L.j > M.nt) {
           L.phase = PH_DONE;
@@ -344,7 +414,12 @@ __device__ __forceinline__ void advance(Lane& L) {
         break;
       }
       case PH_DO_SWITCH: {
+        if (L.out_pending) {  // the switch re-lays y out and changes the descriptor the pending output needs
+          L.flush_now = true;
+          return;
+        }
         do_switch(L);
+        L.ynorm_valid = false;
         L.phase = PH_EVOLVE;
         break;
       }
@@ -371,20 +446,24 @@ __device__ __forceinline__ void advance(Lane& L) {
           L.req_tau = L.tau;
           L.req_in = 0;
           L.req_out = 1;
-          L.evaluated = true;
+          L.want_derivs = true;
           L.phase = PH_DV_K1;
           return;
         }
-        L.evaluated = false;
         L.phase = PH_DV_K1;
         break;
       }
       case PH_DV_K1: {  // step-size selection, camb/subroutines.f90:800-925, then stage 2 input
         const int n = e.neq;
-        const double* y = col(L, 0);
         const double x = L.tau, xend = L.target;
-        double temp = 0.0;
-        for (int i = 1; i <= n; i++) temp = fmax(temp, fabs(AT(y, i)));
+        double temp = L.ynorm;
+        if (!L.ynorm_valid) {  // first step after initial() or a switch; otherwise the final row keeps it current
+          const double* y = col(L, 0);
+          temp = 0.0;
+          for (int i = 1; i <= n; i++) temp = fmax(temp, fabs(AT(y, i)));
+          L.ynorm = temp;
+          L.ynorm_valid = true;
+        }
         const double c12 = fmin(temp, 1.0);
         L.hmin = 10.0 * fmax(1.e-35, 1.3877787807814457e-17 * fmax(c12 / tol, fabs(x)));  // rreb = 2^-56
         const double hmax = 2.0;
@@ -413,29 +492,21 @@ __device__ __forceinline__ void advance(Lane& L) {
           L.xtrial = x + copysign(L.hmag, xend - x);
         }
         L.htrial = L.xtrial - x;
-        temp = L.htrial / 1398169080000.0;
-        const double* w1 = col(L, 1);
-        double* w9 = col(L, 9);
-        for (int i = 1; i <= n; i++) AT(w9, i) = AT(y, i) + temp * AT(w1, i) * 233028180000.0;
+        L.crow = 0;
         L.req_tau = x + L.htrial / 6.0;
         L.req_in = 9;
         L.req_out = 2;
+        L.want_derivs = true;
         L.stage = 2;
         L.phase = PH_DV_STAGE;
         return;
       }
       case PH_DV_STAGE: {
-        const int n = e.neq;
         const int s = L.stage;  // the stage whose derivative has just been written (2..8)
-        const double* y = col(L, 0);
-        double* w9 = col(L, 9);
         const double x = L.tau;
-        const double temp = L.htrial / 1398169080000.0;
         if (s < 8) {
-          // input of stage s+1 : row s-1 of the tableau.  One specialised, 4-way batched loop per stage so that
-          // the (1 + #columns) x 4 independent loads of a batch are in flight together (the columns live in
-          // L2/HBM; a one-element-at-a-time loop stalls on every element).
-          stage_input(L, s - 1, n, temp);
+          // input of stage s+1 : row s-1 of the tableau, formed by the warp-wide combine()
+          L.crow = s - 1;
           double frac;
           switch (s) {
             case 2: frac = 4.0 / 15.0; break;
@@ -453,52 +524,32 @@ __device__ __forceinline__ void advance(Lane& L) {
             L.req_tau = x + L.htrial * frac;
           L.req_in = 9;
           L.req_out = s + 1;
+          L.want_derivs = true;
           L.stage = s + 1;
           return;
         }
-        // s == 8: solution, error estimate, accept/reject (camb/subroutines.f90:995-1110)
-        const double *w1 = col(L, 1), *w3 = col(L, 3), *w4 = col(L, 4), *w5 = col(L, 5), *w6 = col(L, 6), *w7 = col(L, 7),
-                     *w8 = col(L, 8);
-        double errn = 0.0;
-        {
-          int i = 1;
-          for (; i + 1 <= n; i += 2) {  // 2-way batched: 2 x 8 independent loads in flight
-            double v[2][8];
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-              v[u][0] = AT(y, i + u); v[u][1] = AT(w1, i + u); v[u][2] = AT(w3, i + u); v[u][3] = AT(w4, i + u);
-              v[u][4] = AT(w5, i + u); v[u][5] = AT(w6, i + u); v[u][6] = AT(w7, i + u); v[u][7] = AT(w8, i + u);
-            }
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-              AT(w9, i + u) = v[u][0] + temp * (v[u][1] * 104862681000.0 + v[u][2] * 545186250000.0 + v[u][3] * 446637345000.0 +
-                                               v[u][4] * 188806464000.0 + v[u][6] * 15076875000.0 + v[u][7] * 97599465000.0);
-              const double w2 = (v[u][1] * 8738556750.0 + v[u][2] * 9735468750.0 - v[u][3] * 9709507500.0 + v[u][4] * 8582112000.0 +
-                                 v[u][5] * 95329710000.0 - v[u][6] * 15076875000.0 - v[u][7] * 97599465000.0) /
-                                1398169080000.0;
-              errn = fmax(errn, fabs(w2) / fmax(1.0, fabs(v[u][0])));
-            }
-          }
-          for (; i <= n; i++) {
-            AT(w9, i) = AT(y, i) + temp * (AT(w1, i) * 104862681000.0 + AT(w3, i) * 545186250000.0 + AT(w4, i) * 446637345000.0 +
-                                           AT(w5, i) * 188806464000.0 + AT(w7, i) * 15076875000.0 + AT(w8, i) * 97599465000.0);
-            const double w2 = (AT(w1, i) * 8738556750.0 + AT(w3, i) * 9735468750.0 - AT(w4, i) * 9709507500.0 +
-                               AT(w5, i) * 8582112000.0 + AT(w6, i) * 95329710000.0 - AT(w7, i) * 15076875000.0 -
-                               AT(w8, i) * 97599465000.0) /
-                              1398169080000.0;
-            errn = fmax(errn, fabs(w2) / fmax(1.0, fabs(AT(y, i))));
-          }
-        }
-        L.est = errn * L.hmag * 1.0;
+        // s == 8: trial solution and error vector (row 7), then PH_DV_FINAL
+        L.crow = 7;
+        L.phase = PH_DV_FINAL;
+        return;
+      }
+      case PH_DV_FINAL: {  // accept/reject, camb/subroutines.f90:1021-1110
+        const int n = e.neq;
+        L.est = L.errn * L.hmag * 1.0;
         L.ind = 5;
         if (L.est > tol) L.ind = 6;
-        for (int c = 2; c <= 8; c++) discard_rows(col(L, c), n);
         if (L.ind != 6) {
           L.tau = L.xtrial;
-          double* yw = col(L, 0);
-          for (int i = 1; i <= n; i++) AT(yw, i) = AT(w9, i);
-          discard_rows(w9, n);
-          discard_rows(col(L, 1), n);  // k1 is re-evaluated at the start of the next step
+          if (L.sm && L.sm_cols == 1) {
+            // latency mode with one shared-memory column: the stage input (read by derivs with dependent loads)
+            // stays the shared one, so y is copied as dverk does
+            double* yw = col(L, 0);
+            const double* w9 = col(L, 9);
+            for (int i = 1; i <= n; i++) AT(yw, i) = AT(w9, i);
+          } else {
+            L.ysel ^= 1;  // y <- w9 : the columns trade places
+          }
+          L.ynorm = L.ynorm_new;
           L.nfail = 0.0;
           if (L.tau == L.target) {
             L.ind = 3;
@@ -508,7 +559,6 @@ __device__ __forceinline__ void advance(Lane& L) {
             break;
           }
         } else {
-          discard_rows(w9, n);
           L.nfail = L.nfail + 1.0;
           if (!(L.hmag > L.hmin)) {
             L.status = 4;  // dverk ind=-3 -> error_evolution (camb/equations_galileon.f90:285-292)
@@ -520,18 +570,25 @@ __device__ __forceinline__ void advance(Lane& L) {
         break;
       }
       case PH_OUT_REQ: {  // camb/equations_galileon.f90:1296-1297
-        double* yp = col(L, 2);
+        if (L.out_pending) {  // one pending output per lane
+          L.flush_now = true;
+          return;
+        }
+        double* yp = col(L, 11);
         for (int i = 1; i <= e.nvar; i++) AT(yp, i) = 0;
         L.req_tau = L.tau;
         L.req_in = 0;
-        L.req_out = 2;
+        L.req_out = 11;
+        L.want_derivs = true;
         L.phase = PH_OUT_DONE;
         return;
       }
-      case PH_OUT_DONE: {
-        double src[3] = {0, 0, 0};
-        output_sources(L.M, &L.e, col(L, 0), col(L, 2), M.ts + (size_t)(L.j - 1) * 8, L.tau, src);
-        for (int s = 0; s < S; s++) M.Src[((size_t)(L.j - 1) * S + s) * M.nk + L.kidx] = src[s];
+      case PH_OUT_DONE: {  // the sources themselves are formed by flush_output()
+        L.out_pending = true;
+        L.out_stashed = false;
+        L.out_j = L.j;
+        L.out_pig = e.pig;
+        L.out_pigdot = e.pigdot;
         L.n_out++;
         L.phase = PH_NEXT_OUTPUT;
         break;
@@ -559,6 +616,17 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
   L.phase = PH_DONE;
   L.status = 0;
   L.n_derivs = L.sum_n = L.n_out = 0;
+  L.want_derivs = false;
+  L.out_pending = L.out_stashed = L.flush_now = false;
+  L.crow = -1;
+  L.ysel = 0;
+  L.ynorm_valid = false;
+  L.ynorm = L.ynorm_new = L.errn = 0;
+  L.NV = NV;
+  L.ws = workspace;
+  L.sm = nullptr;
+  L.sm_cols = 0;
+  L.e.neq = 0;
   if (have) {
     const int2 it = items[tid];
     L.M = models + it.x;
@@ -626,19 +694,34 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
   // instructions (far beyond the 32 KB L1.5 instruction cache), so warps that reach derivs() at the same time
   // share one instruction stream from L2 instead of fetching it once per warp.
   for (;;) {
-    if (L.phase != PH_DONE) advance(L);
-    const bool need = L.phase != PH_DONE;
+    // control flow up to the next RHS request.  A lane normally needs one pass: advance() leaves a stage
+    // combination (and the request that follows it) pending, combine() forms it for the whole warp.  After the last
+    // stage the accept/reject logic needs the combination's result first, hence a second pass; a lane that has to
+    // wait for flush_output() takes one more.
+    for (;;) {
+      const bool run = !L.want_derivs && L.crow < 0 && L.phase != PH_DONE;
+      if (!__any_sync(0xffffffffu, run)) break;
+      if (run) advance(L);
+      if (__any_sync(0xffffffffu, L.flush_now)) {
+        if (L.out_pending) flush_output(L);
+        L.flush_now = false;
+      }
+      if (__any_sync(0xffffffffu, L.crow >= 0)) combine(L);
+    }
+    const bool need = L.want_derivs;
+    const bool alive = L.phase != PH_DONE || need;
     if (blockDim.x > 32) {
-      if (!__syncthreads_or(need)) break;
+      if (!__syncthreads_or(alive)) break;
     } else {
-      if (!__any_sync(0xffffffffu, need)) break;
+      if (!__any_sync(0xffffffffu, alive)) break;
     }
     if (need) {
-      #if GC_HOT_IN_SMEM
+#if GC_HOT_IN_SMEM
       derivs(reinterpret_cast<const DevModel*>(L.hot), &L.e, L.req_tau, col(L, L.req_in), col(L, L.req_out));
 #else
       derivs(L.M, &L.e, L.req_tau, col(L, L.req_in), col(L, L.req_out));
 #endif
+      L.want_derivs = false;
       L.n_derivs++;
       L.sum_n += L.e.neq;
     }
@@ -646,13 +729,15 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
   if (tid < nitems && !have) status[tid] = 0;
   if (have) {
     status[tid] = L.status;
-    atomicAdd(&counters[0], L.n_derivs);
-    atomicAdd(&counters[1], L.sum_n);
-    atomicAdd(&counters[2], L.n_out);
+    atomicAdd(&counters[0], (unsigned long long)L.n_derivs);
+    atomicAdd(&counters[1], (unsigned long long)L.sum_n);
+    atomicAdd(&counters[2], (unsigned long long)L.n_out);
   }
 }
 
 }  // namespace gc
+
+extern "C" int gc_lane_stride() { return (int)GC_LANE_STRIDE; }
 
 extern "C" void gc_upload_constants() {
   double denl[260], polfac[260];

@@ -17,7 +17,7 @@
 #include "model.h"
 
 #define GC_LANES 32
-#define GC_NCOL 10  // column 0 = y, columns 1..9 = dverk w(:,1..9)
+#define GC_NCOL 12  // column 0 = y, columns 1..9 = dverk w(:,1..9), 10 = y of a pending output, 11 = its y'
 
 __constant__ double c_denl[260];    // 1/(2l+1)            camb/equations_galileon.f90:525-527
 __constant__ double c_polfac[260];  // (l+3)(l-1)/(l+1)    camb/equations_galileon.f90:516-520

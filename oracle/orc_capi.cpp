@@ -108,6 +108,10 @@ int orc_stage_bessels(void* h) {
   GenerateBessels(M);
   return 0;
 }
+int orc_stage_qgrid(void* h) {  // the integration k grid alone (host pre-stage of the GPU path)
+  SetkValuesForInt(*(Model*)h);
+  return 0;
+}
 int orc_stage_los(void* h) {
   Model& M = *(Model*)h;
   SetkValuesForInt(M);

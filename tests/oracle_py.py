@@ -32,7 +32,7 @@ def lib():
         L.orc_set_physical.argtypes = [C.c_void_p] + [C.c_double] * 4
         L.orc_load_template.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_run.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
-        for s in ("background", "initvars", "sources", "spline_k", "bessels", "los", "cls", "lensing"):
+        for s in ("background", "initvars", "sources", "spline_k", "bessels", "los", "cls", "lensing", "qgrid"):
             getattr(L, "orc_stage_" + s).argtypes = [C.c_void_p]
         L.orc_alloc_sources.argtypes = [C.c_void_p]
         L.orc_source_k.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]

@@ -123,7 +123,7 @@ def test_lensing_stage_alone_high_l(gpu):
     P2 = dict(P)
     P2.update(AccuracyBoost=2)
     oB = Oracle(lmax=5000, **P2)
-    oB.stage("background", "initvars")
+    oB.stage("background", "initvars", "qgrid")
     oB.put("Cl", Cl)
     oB.stage("lensing")
     Lo = oB.Cl_lensed()

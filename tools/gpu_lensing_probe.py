@@ -24,7 +24,7 @@ for lmax, ab, batch in zip(args[0::3], args[1::3], args[2::3]):
     oA.run()
     P2 = dict(GAL, AccuracyBoost=ab)
     oB = Oracle(lmax=lmax, **P2)
-    oB.stage("background", "initvars")
+    oB.stage("background", "initvars", "qgrid")
     oB.put("Cl", oA.Cl())
     t0 = time.time()
     oB.stage("lensing")
