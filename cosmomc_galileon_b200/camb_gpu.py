@@ -168,6 +168,7 @@ def load_library():
         L.galcamb_batch_lensed_cls_.argtypes = [C.POINTER(CModel), C.POINTER(_I), C.c_void_p, C.POINTER(_I), C.c_void_p]
         L.galcamb_get_timings_.argtypes = [C.c_void_p]
         L.galcamb_get_counters_.argtypes = [C.c_void_p]
+        L.galcamb_get_evolve_stats_.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -319,6 +320,11 @@ class GalCamb:
         ms = np.zeros(8)
         self.L.galcamb_get_timings_(ms.ctypes.data)
         return dict(zip("evolve spline_k los cls lensing unused bessel total".split(), ms))
+
+    def evolve_stats(self):
+        c = np.zeros(2)
+        self.L.galcamb_get_evolve_stats_(c.ctypes.data)
+        return dict(zip("rhs_executed outputs_from_k1".split(), c))
 
     def counters(self):
         c = np.zeros(4)

@@ -97,6 +97,7 @@ struct Ctx {
   std::vector<int2> items;
   double ms[8] = {0};
   double counters[4] = {0};
+  double evolve_stats[2] = {0};
   std::string err;
 };
 
@@ -561,15 +562,20 @@ int galcamb_evolve_sources_(void) {
   CK(cudaEventRecord(g.ev[1], g.stream));
   std::vector<int> st(nitems);
   CK(cudaMemcpyAsync(st.data(), g.d_status, nitems * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-  unsigned long long c[4];
-  CK(cudaMemcpyAsync(c, g.d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
+  unsigned long long c[5];
+  CK(cudaMemcpyAsync(c, g.d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]);
   g.ms[0] = ms;
-  g.counters[0] = (double)c[0];
+  // c[0] counts the evaluations executed; the reference algorithm also evaluates y' once per output
+  // (camb/equations_galileon.f90:1297), which K1 takes from the next step's k1 (c[4] outputs): the algorithmic
+  // count of SURVEY.md section 8d is their sum
+  g.counters[0] = (double)(c[0] + c[4]);
   g.counters[1] = (double)c[1];
   g.counters[2] = (double)c[2];
+  g.evolve_stats[0] = (double)c[0];
+  g.evolve_stats[1] = (double)c[4];
   int rc = 0;
   for (int i = 0; i < nitems; i++)
     if (st[i] && g.items[i].x >= 0) {
@@ -839,6 +845,12 @@ int galcamb_batch_lensed_cls_(const galcamb_model* models, const int* nmodels, d
 int galcamb_get_timings_(double* ms) {
   for (int i = 0; i < 8; i++) ms[i] = g.ms[i];
   ms[7] = g.ms[0] + g.ms[1] + g.ms[2] + g.ms[3];  // the unlensed path; ms[4] = lensing
+  return 0;
+}
+
+int galcamb_get_evolve_stats_(double* s) {
+  s[0] = g.evolve_stats[0];
+  s[1] = g.evolve_stats[1];
   return 0;
 }
 

@@ -35,6 +35,7 @@ enum Phase : int {
   PH_DV_K1,
   PH_DV_STAGE,
   PH_DV_FINAL,
+  PH_OUT_MARK,
   PH_OUT_REQ,
   PH_OUT_DONE,
   PH_DONE
@@ -71,12 +72,12 @@ struct Lane {
   int ysel;  // which physical column (0 or 9) currently holds y; the other one is the stage input w9
   // deferred output (see flush_output): the sources of output time out_j are formed later, together with the other
   // lanes' pending outputs, from y (stashed in column 10 by the next combine()), y' (column 11) and these scalars
-  bool out_pending, out_stashed, flush_now;
-  int out_j;
+  bool out_pending, out_stashed, flush_now, out_need_k1, stash_k1, waiting;
+  int out_j, resume_phase;
   double out_pig, out_pigdot;
   int status;
   // work counters
-  unsigned n_derivs, sum_n, n_out;  // per lane: < 1e5 evaluations of < 200 equations
+  unsigned n_derivs, sum_n, n_out, n_shared;  // per lane: < 1e5 evaluations of < 200 equations
 #if GC_HOT_IN_SMEM
   // private copy of the model's hot block (the prefix of DevModel that derivs() and its helpers read): in batch mode
   // the 32 lanes of a warp belong to 32 different models, so reading the constants from the DevModel array costs 32
@@ -158,6 +159,8 @@ __device__ __forceinline__ void combine(Lane& L) {
   // a lane whose last output is still pending keeps a copy of that y (this is the first pass over y since then)
   const bool stash = on && L.out_pending && !L.out_stashed;
   double* __restrict__ ys = L.ws + (size_t)10 * L.NV * GC_LANES;
+  const bool stash_k1 = stash && L.stash_k1;  // row 0 only: kv[0] is the k1 the output shares
+  double* __restrict__ ks = L.ws + (size_t)11 * L.NV * GC_LANES;
   for (int i = 1; i <= nmax; i += 4) {
     // all loads of the batch first (up to 4 + 8 x 4 independent loads in flight), then the arithmetic, then the stores
     double yv[4], kv[8][4];
@@ -199,6 +202,7 @@ __device__ __forceinline__ void combine(Lane& L) {
         const double v = (r == 0) ? yv[u] + temp * kv[0][u] * 233028180000.0 : yv[u] + temp * a1[u];
         AT(w9, i + u) = v;
         if (stash) AT(ys, i + u) = yv[u];
+        if (stash_k1) AT(ks, i + u) = kv[0][u];
         if (fin) {
           const double w2 = a2[u] / 1398169080000.0;
           errn = fmax(errn, fabs(w2) / fmax(1.0, fabs(yv[u])));
@@ -211,7 +215,10 @@ __device__ __forceinline__ void combine(Lane& L) {
     L.errn = errn;
     L.ynorm_new = ynew;
   }
-  if (stash) L.out_stashed = true;
+  if (stash) {
+    L.out_stashed = true;
+    L.stash_k1 = false;
+  }
   L.crow = -1;
 }
 
@@ -228,8 +235,11 @@ __device__ __forceinline__ void flush_output(Lane& L) {
   L.e.pig = L.out_pig;
   L.e.pigdot = L.out_pigdot;
   double src[3] = {0, 0, 0};
+  // not yet copied aside (the flush came before the step's first combine): y and the shared k1 are still in place
   const double* y = L.out_stashed ? L.ws + (size_t)10 * L.NV * GC_LANES : col(L, 0);
-  output_sources(L.M, &L.e, y, col(L, 11), M.ts + (size_t)(L.out_j - 1) * 8, M.ts[(size_t)(L.out_j - 1) * 8], src);
+  const double* yp = (!L.out_stashed && L.stash_k1) ? col(L, 1) : col(L, 11);
+  L.stash_k1 = false;
+  output_sources(L.M, &L.e, y, yp, M.ts + (size_t)(L.out_j - 1) * 8, M.ts[(size_t)(L.out_j - 1) * 8], src);
   for (int s = 0; s < S; s++) M.Src[((size_t)(L.out_j - 1) * S + s) * M.nk + L.kidx] = src[s];
   L.e.pig = pig;
   L.e.pigdot = pigdot;
@@ -367,7 +377,7 @@ __device__ inline void do_switch(Lane& L) {
 }
 
 // Run the lane's control flow until it needs derivs() (returns with L.req_* set) or finishes.
-__device__ __forceinline__ void advance(Lane& L) {
+__device__ __forceinline__ void advance(Lane& L, int wphase, bool align) {
   const DevModel& M = *L.M;
   EV& e = L.e;
   const int S = M.SourceNum;
@@ -375,18 +385,30 @@ __device__ __forceinline__ void advance(Lane& L) {
   for (;;) {
     switch (L.phase) {
       case PH_NEXT_OUTPUT: {
-        if (L.j + 1 > M.nt && L.out_pending) {  // the last output must be out before the lane retires
-          L.flush_now = true;
-          return;
+        const int jn = L.j + 1;
+        const bool stops = jn > M.nt;
+        double tauend = 0;
+        bool zero = false;
+        if (!stops) {
+          tauend = M.ts[(size_t)(jn - 1) * 8];
+          zero = (e.q * tauend > M.max_etak_scalar && tauend > M.taurend) && !M.WantLateTime;  // camb/cmbmain.f90:1034-1036
         }
-        L.j++;
-        if (L.j > M.nt) {
+        if ((stops || zero) && L.out_need_k1) {  // no further step from this state: evaluate y' for the output now
+          L.resume_phase = PH_NEXT_OUTPUT;
+          L.phase = PH_OUT_REQ;
+          break;
+        }
+        if (stops) {
+          if (L.out_pending) {  // the last output must be out before the lane retires
+            L.flush_now = true;
+            return;
+          }
+          L.j = jn;
           L.phase = PH_DONE;
           return;
         }
-        const double tauend = M.ts[(size_t)(L.j - 1) * 8];
-        if ((e.q * tauend > M.max_etak_scalar && tauend > M.taurend) && !M.WantLateTime) {
-          // camb/cmbmain.f90:1034-1036
+        L.j = jn;
+        if (zero) {
           for (int s = 0; s < S; s++) M.Src[((size_t)(L.j - 1) * S + s) * M.nk + L.kidx] = 0;
           break;
         }
@@ -414,6 +436,11 @@ __device__ __forceinline__ void advance(Lane& L) {
         break;
       }
       case PH_DO_SWITCH: {
+        if (L.out_need_k1) {  // the next k1 will be taken with the new layout: evaluate y' for the output now
+          L.resume_phase = PH_DO_SWITCH;
+          L.phase = PH_OUT_REQ;
+          break;
+        }
         if (L.out_pending) {  // the switch re-lays y out and changes the descriptor the pending output needs
           L.flush_now = true;
           return;
@@ -442,6 +469,14 @@ __device__ __forceinline__ void advance(Lane& L) {
         break;
       }
       case PH_DV_LOOP: {
+        // Warp alignment: every trial step is 8 RHS evaluations, so lanes that all start their steps in rounds with
+        // wphase == 0 sit in the same Runge-Kutta stage in every round -- same tableau row in combine(), same
+        // branch of this state machine -- no matter how many steps each lane needs.  A lane that fell out of step
+        // (explicit output evaluation, rejected step) sits out until the next such round.
+        if (align && wphase != 0) {
+          L.waiting = true;
+          return;
+        }
         if (L.ind != 6) {
           L.req_tau = L.tau;
           L.req_in = 0;
@@ -450,10 +485,24 @@ __device__ __forceinline__ void advance(Lane& L) {
           L.phase = PH_DV_K1;
           return;
         }
-        L.phase = PH_DV_K1;
+        L.phase = PH_DV_K1;  // rejected step: k1 is still valid (camb/subroutines.f90:1095-1110)
+        if (align) {
+          L.waiting = true;
+          return;
+        }
         break;
       }
       case PH_DV_K1: {  // step-size selection, camb/subroutines.f90:800-925, then stage 2 input
+        if (L.out_need_k1) {
+          // the k1 just evaluated at (tau, y) IS the y' that output() evaluates at :1297 -- same state, same
+          // descriptor -- so the output shares it; combine() copies it (and y) aside for flush_output()
+          L.out_pig = e.pig;
+          L.out_pigdot = e.pigdot;
+          L.out_need_k1 = false;
+          L.stash_k1 = true;
+          L.n_shared++;
+          L.sum_n += e.neq;
+        }
         const int n = e.neq;
         const double x = L.tau, xend = L.target;
         double temp = L.ynorm;
@@ -555,7 +604,7 @@ __device__ __forceinline__ void advance(Lane& L) {
             L.ind = 3;
             L.c20 = L.target;
             L.c21 = 1.0;
-            L.phase = L.after_switch ? PH_DO_SWITCH : PH_OUT_REQ;
+            L.phase = L.after_switch ? PH_DO_SWITCH : PH_OUT_MARK;
             break;
           }
         } else {
@@ -569,11 +618,20 @@ __device__ __forceinline__ void advance(Lane& L) {
         L.phase = PH_DV_LOOP;
         break;
       }
-      case PH_OUT_REQ: {  // camb/equations_galileon.f90:1296-1297
+      case PH_OUT_MARK: {  // an output time has been reached (camb/cmbmain.f90:1038 -> output)
         if (L.out_pending) {  // one pending output per lane
           L.flush_now = true;
           return;
         }
+        L.out_pending = true;
+        L.out_stashed = false;
+        L.out_need_k1 = true;
+        L.out_j = L.j;
+        L.n_out++;
+        L.phase = PH_NEXT_OUTPUT;
+        break;
+      }
+      case PH_OUT_REQ: {  // explicit y' evaluation, camb/equations_galileon.f90:1296-1297
         double* yp = col(L, 11);
         for (int i = 1; i <= e.nvar; i++) AT(yp, i) = 0;
         L.req_tau = L.tau;
@@ -584,13 +642,10 @@ __device__ __forceinline__ void advance(Lane& L) {
         return;
       }
       case PH_OUT_DONE: {  // the sources themselves are formed by flush_output()
-        L.out_pending = true;
-        L.out_stashed = false;
-        L.out_j = L.j;
         L.out_pig = e.pig;
         L.out_pigdot = e.pigdot;
-        L.n_out++;
-        L.phase = PH_NEXT_OUTPUT;
+        L.out_need_k1 = false;
+        L.phase = L.resume_phase;
         break;
       }
       default:
@@ -615,9 +670,10 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
   const bool have = tid < nitems && items[tid < nitems ? tid : 0].x >= 0;  // padding items carry model = -1
   L.phase = PH_DONE;
   L.status = 0;
-  L.n_derivs = L.sum_n = L.n_out = 0;
+  L.n_derivs = L.sum_n = L.n_out = L.n_shared = 0;
   L.want_derivs = false;
-  L.out_pending = L.out_stashed = L.flush_now = false;
+  L.out_pending = L.out_stashed = L.flush_now = L.out_need_k1 = L.stash_k1 = L.waiting = false;
+  L.resume_phase = PH_DONE;
   L.crow = -1;
   L.ysel = 0;
   L.ynorm_valid = false;
@@ -693,17 +749,20 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
   // All warps of the CTA run the RHS evaluation together: the kernel's hot loop is ~8k straight-line
   // instructions (far beyond the 32 KB L1.5 instruction cache), so warps that reach derivs() at the same time
   // share one instruction stream from L2 instead of fetching it once per warp.
-  for (;;) {
+  const bool align = __popc(__ballot_sync(0xffffffffu, have)) > 1;
+  int wphase = 0;
+  for (;; wphase = (wphase + 1) & 7) {
     // control flow up to the next RHS request.  A lane normally needs one pass: advance() leaves a stage
     // combination (and the request that follows it) pending, combine() forms it for the whole warp.  After the last
     // stage the accept/reject logic needs the combination's result first, hence a second pass; a lane that has to
     // wait for flush_output() takes one more.
+    L.waiting = false;
     for (;;) {
-      const bool run = !L.want_derivs && L.crow < 0 && L.phase != PH_DONE;
+      const bool run = !L.want_derivs && L.crow < 0 && L.phase != PH_DONE && !L.waiting;
       if (!__any_sync(0xffffffffu, run)) break;
-      if (run) advance(L);
+      if (run) advance(L, wphase, align);
       if (__any_sync(0xffffffffu, L.flush_now)) {
-        if (L.out_pending) flush_output(L);
+        if (L.out_pending && !L.out_need_k1) flush_output(L);
         L.flush_now = false;
       }
       if (__any_sync(0xffffffffu, L.crow >= 0)) combine(L);
@@ -732,6 +791,7 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
     atomicAdd(&counters[0], (unsigned long long)L.n_derivs);
     atomicAdd(&counters[1], (unsigned long long)L.sum_n);
     atomicAdd(&counters[2], (unsigned long long)L.n_out);
+    atomicAdd(&counters[4], (unsigned long long)L.n_shared);
   }
 }
 

@@ -138,6 +138,9 @@ int galcamb_batch_lensed_cls_(const galcamb_model* models, const int* nmodels, d
  * algorithmic work counters of SURVEY.md section 8(d). */
 int galcamb_get_timings_(double* ms /*[8]: evolve, spline_k, los, cls, lensing, -, bessel, total of 0..3*/);
 int galcamb_get_counters_(double* c /*[4]: n_derivs, sum_n, n_out, n_iter*/);
+/* K1 executes fewer RHS evaluations than the reference algorithm counts in n_derivs: the y' of an output time
+ * (camb/equations_galileon.f90:1297) is the k1 of the next step.  s[0] = evaluations executed, s[1] = outputs served so. */
+int galcamb_get_evolve_stats_(double* s /*[2]*/);
 int galcamb_sync_(void);
 /* FP64 FMA micro-benchmark (roofline denominator): out[0] = device peak TFLOP/s, out[1], out[2] = one warp per SM with
  * 1 and 4 dependent chains (latency probes) */
