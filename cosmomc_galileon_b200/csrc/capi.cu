@@ -562,8 +562,8 @@ int galcamb_evolve_sources_(void) {
   CK(cudaEventRecord(g.ev[1], g.stream));
   std::vector<int> st(nitems);
   CK(cudaMemcpyAsync(st.data(), g.d_status, nitems * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-  unsigned long long c[5];
-  CK(cudaMemcpyAsync(c, g.d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
+  unsigned long long c[8];
+  CK(cudaMemcpyAsync(c, g.d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]);
@@ -576,6 +576,9 @@ int galcamb_evolve_sources_(void) {
   g.counters[2] = (double)c[2];
   g.evolve_stats[0] = (double)c[0];
   g.evolve_stats[1] = (double)c[4];
+  if (getenv("GALCAMB_PHASE_PROFILE"))  // only meaningful for a -DGC_PROFILE_PHASES build: warp-cycles per phase
+    fprintf(stderr, "[galcamb] warp-cycles: advance %.3e combine %.3e flush+loop %.3e barrier+derivs %.3e\n", (double)c[5],
+            (double)c[6], (double)c[3], (double)c[7]);
   int rc = 0;
   for (int i = 0; i < nitems; i++)
     if (st[i] && g.items[i].x >= 0) {

@@ -161,24 +161,46 @@ __device__ __forceinline__ void combine(Lane& L) {
   double* __restrict__ ys = L.ws + (size_t)10 * L.NV * GC_LANES;
   const bool stash_k1 = stash && L.stash_k1;  // row 0 only: kv[0] is the k1 the output shares
   double* __restrict__ ks = L.ws + (size_t)11 * L.NV * GC_LANES;
+  // warp-uniform fast path: every lane forms the same row (the normal state of an aligned warp) -> no per-lane column
+  // predicates; full batches below the shortest lane's length need no range predicates either
+  const bool same_row = __all_sync(0xffffffffu, cmask == umask);
+  const int nmin = __reduce_min_sync(0xffffffffu, on ? n : 0x7fffffff);
   for (int i = 1; i <= nmax; i += 4) {
     // all loads of the batch first (up to 4 + 8 x 4 independent loads in flight), then the arithmetic, then the stores
     double yv[4], kv[8][4];
     bool p[4];
+    if (same_row && i + 3 <= nmin) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      p[u] = i + u <= n;
-      yv[u] = p[u] ? AT(y, i + u) : 0.0;
-    }
+      for (int u = 0; u < 4; u++) {
+        p[u] = true;
+        yv[u] = AT(y, i + u);
+      }
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-      if (umask & (1u << c)) {
-        const bool mine = (cmask >> c) & 1u;
+      for (int c = 0; c < 8; c++) {
+        if (umask & (1u << c)) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) kv[c][u] = (mine && p[u]) ? AT(kc[c], i + u) : 0.0;
-      } else {
+          for (int u = 0; u < 4; u++) kv[c][u] = AT(kc[c], i + u);
+        } else {
 #pragma unroll
-        for (int u = 0; u < 4; u++) kv[c][u] = 0.0;
+          for (int u = 0; u < 4; u++) kv[c][u] = 0.0;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        p[u] = i + u <= n;
+        yv[u] = p[u] ? AT(y, i + u) : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        if (umask & (1u << c)) {
+          const bool mine = (cmask >> c) & 1u;
+#pragma unroll
+          for (int u = 0; u < 4; u++) kv[c][u] = (mine && p[u]) ? AT(kc[c], i + u) : 0.0;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; u++) kv[c][u] = 0.0;
+        }
       }
     }
     double a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
@@ -757,16 +779,39 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
     // stage the accept/reject logic needs the combination's result first, hence a second pass; a lane that has to
     // wait for flush_output() takes one more.
     L.waiting = false;
+#ifdef GC_PROFILE_PHASES
+    long long t0 = clock64(), t_adv = 0, t_flush = 0, t_comb = 0;
+#endif
     for (;;) {
       const bool run = !L.want_derivs && L.crow < 0 && L.phase != PH_DONE && !L.waiting;
       if (!__any_sync(0xffffffffu, run)) break;
+#ifdef GC_PROFILE_PHASES
+      long long ta = clock64();
+#endif
       if (run) advance(L, wphase, align);
+#ifdef GC_PROFILE_PHASES
+      __syncwarp();
+      long long tb = clock64();
+      t_adv += tb - ta;
+#endif
       if (__any_sync(0xffffffffu, L.flush_now)) {
         if (L.out_pending && !L.out_need_k1) flush_output(L);
         L.flush_now = false;
       }
+#ifdef GC_PROFILE_PHASES
+      __syncwarp();
+      long long tc = clock64();
+      t_flush += tc - tb;
+#endif
       if (__any_sync(0xffffffffu, L.crow >= 0)) combine(L);
+#ifdef GC_PROFILE_PHASES
+      __syncwarp();
+      t_comb += clock64() - tc;
+#endif
     }
+#ifdef GC_PROFILE_PHASES
+    long long t1 = clock64();
+#endif
     const bool need = L.want_derivs;
     const bool alive = L.phase != PH_DONE || need;
     if (blockDim.x > 32) {
@@ -784,6 +829,16 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
       L.n_derivs++;
       L.sum_n += L.e.neq;
     }
+#ifdef GC_PROFILE_PHASES
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+      long long t2 = clock64();
+      atomicAdd(&counters[5], (unsigned long long)t_adv);
+      atomicAdd(&counters[6], (unsigned long long)t_comb);
+      atomicAdd(&counters[7], (unsigned long long)(t2 - t1));        // barrier + derivs
+      atomicAdd(&counters[3], (unsigned long long)((t1 - t0) - t_adv - t_comb));  // flush + loop overhead
+    }
+#endif
   }
   if (tid < nitems && !have) status[tid] = 0;
   if (have) {
