@@ -163,26 +163,66 @@ __device__ __forceinline__ void combine(Lane& L) {
   double* __restrict__ ks = L.ws + (size_t)11 * L.NV * GC_LANES;
   // warp-uniform fast path: every lane forms the same row (the normal state of an aligned warp) -> no per-lane column
   // predicates; full batches below the shortest lane's length need no range predicates either
-  const bool same_row = __all_sync(0xffffffffu, cmask == umask);
+  const bool same_row = __all_sync(0xffffffffu, !on || cmask == umask);
   const int nmin = __reduce_min_sync(0xffffffffu, on ? n : 0x7fffffff);
-  for (int i = 1; i <= nmax; i += 4) {
+  int i = 1;
+  // warp-uniform rows 0..5 read at most the first five derivative columns: 8 elements per batch (8 + 5 x 8 loads in
+  // flight) halve the number of latency-bound batches
+  if (same_row && (umask & 0xe0u) == 0u) {
+    for (; i + 7 <= nmin; i += 8) {
+      double yw[8], kw[5][8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) yw[u] = 0.0;
+#pragma unroll
+      for (int c = 0; c < 5; c++)
+#pragma unroll
+        for (int u = 0; u < 8; u++) kw[c][u] = 0.0;
+      if (on) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) yw[u] = AT(y, i + u);
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+          if (umask & (1u << c)) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) kw[c][u] = AT(kc[c], i + u);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int c = 0; c < 5; c++) acc = acc + kw[c][u] * cf[c];
+          const double v = (r == 0) ? yw[u] + temp * kw[0][u] * 233028180000.0 : yw[u] + temp * acc;
+          AT(w9, i + u) = v;
+          if (stash) AT(ys, i + u) = yw[u];
+          if (stash_k1) AT(ks, i + u) = kw[0][u];
+        }
+      }
+    }
+  }
+  for (; i <= nmax; i += 4) {
     // all loads of the batch first (up to 4 + 8 x 4 independent loads in flight), then the arithmetic, then the stores
     double yv[4], kv[8][4];
     bool p[4];
     if (same_row && i + 3 <= nmin) {
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        p[u] = true;
-        yv[u] = AT(y, i + u);
+        p[u] = on;
+        yv[u] = 0.0;
       }
 #pragma unroll
-      for (int c = 0; c < 8; c++) {
-        if (umask & (1u << c)) {
+      for (int c = 0; c < 8; c++)
 #pragma unroll
-          for (int u = 0; u < 4; u++) kv[c][u] = AT(kc[c], i + u);
-        } else {
+        for (int u = 0; u < 4; u++) kv[c][u] = 0.0;
+      if (on) {  // padding lanes of a short k group sit this out
 #pragma unroll
-          for (int u = 0; u < 4; u++) kv[c][u] = 0.0;
+        for (int u = 0; u < 4; u++) yv[u] = AT(y, i + u);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          if (umask & (1u << c)) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) kv[c][u] = AT(kc[c], i + u);
+          }
         }
       }
     } else {
