@@ -129,6 +129,55 @@ __constant__ double c_err[8] = {8738556750.0,  0, 9735468750.0, -9709507500.0, 8
                                 -15076875000.0, -97599465000.0};
 __constant__ unsigned c_rowmask[8] = {0x01, 0x03, 0x07, 0x0f, 0x1f, 0x1f, 0x5f, 0xfd};
 
+// Stage combination of a warp whose lanes all form the SAME tableau row (the normal state of an aligned warp): the
+// columns the row reads are known per instantiation, the loop body is branch-free and small, and the compiler
+// unrolls/pipelines it so that several batches of (NC+1) x U independent loads are in flight (U = 8 elements for the
+// rows that read up to five columns, 4 for the last two).  Runs over the full batches below nend; the generic loop of combine() finishes the tail.
+//   ROW0: w9 = y + (temp*w1)*c with the reference's association (camb/subroutines.f90:930), plus the copies a pending
+//         output needs;  FIN: trial solution + error vector of the last row (:995-1019).
+template <int NC, int U, bool ROW0, bool FIN>
+__device__ __forceinline__ int combine_uniform(int i, int nend, const double* __restrict__ y, double* __restrict__ w9,
+                                               const double* const* kc, const double* cf, const double* ce, double temp,
+                                               bool stash, bool stash_k1, double* __restrict__ ys,
+                                               double* __restrict__ ks, double& errn, double& ynew) {
+#pragma unroll(U == 4 ? 2 : 1)
+  for (; i + U - 1 <= nend; i += U) {
+    double yv[U], kv[NC][U];
+#pragma unroll
+    for (int u = 0; u < U; u++) yv[u] = AT(y, i + u);
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+      for (int u = 0; u < U; u++) kv[c][u] = AT(kc[c], i + u);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      double v;
+      if (ROW0) {
+        v = yv[u] + temp * kv[0][u] * 233028180000.0;
+      } else {
+        double acc = kv[0][u] * cf[0];
+#pragma unroll
+        for (int c = 1; c < NC; c++) acc = acc + kv[c][u] * cf[c];
+        v = yv[u] + temp * acc;
+      }
+      AT(w9, i + u) = v;
+      if (ROW0) {
+        if (stash) AT(ys, i + u) = yv[u];
+        if (stash_k1) AT(ks, i + u) = kv[0][u];
+      }
+      if (FIN) {
+        double a2 = kv[0][u] * ce[0];
+#pragma unroll
+        for (int c = 1; c < NC; c++) a2 = a2 + kv[c][u] * ce[c];
+        const double w2 = a2 / 1398169080000.0;
+        errn = fmax(errn, fabs(w2) / fmax(1.0, fabs(yv[u])));
+        ynew = fmax(ynew, fabs(v));
+      }
+    }
+  }
+  return i;
+}
+
 // ONE stage-combination routine for every row of the tableau, executed by the whole warp together: each lane brings
 // its own row (L.crow), length and scale, so lanes that sit in different Runge-Kutta stages -- the normal state of
 // a warp whose 32 lanes integrate 32 different cosmologies -- share one pass over the columns instead of running
@@ -166,66 +215,41 @@ __device__ __forceinline__ void combine(Lane& L) {
   const bool same_row = __all_sync(0xffffffffu, !on || cmask == umask);
   const int nmin = __reduce_min_sync(0xffffffffu, on ? n : 0x7fffffff);
   int i = 1;
-  // warp-uniform rows 0..5 read at most the first five derivative columns: 8 elements per batch (8 + 5 x 8 loads in
-  // flight) halve the number of latency-bound batches
-  if (same_row && (umask & 0xe0u) == 0u) {
-    for (; i + 7 <= nmin; i += 8) {
-      double yw[8], kw[5][8];
+  if (same_row && nmin >= 4 && nmin != 0x7fffffff) {
+    // compact column list of the row (ascending j, as the sums run)
+    const double* kk[7];
+    double cfk[7], cek[7];
+    int nc = 0;
 #pragma unroll
-      for (int u = 0; u < 8; u++) yw[u] = 0.0;
-#pragma unroll
-      for (int c = 0; c < 5; c++)
-#pragma unroll
-        for (int u = 0; u < 8; u++) kw[c][u] = 0.0;
-      if (on) {
-#pragma unroll
-        for (int u = 0; u < 8; u++) yw[u] = AT(y, i + u);
-#pragma unroll
-        for (int c = 0; c < 5; c++) {
-          if (umask & (1u << c)) {
-#pragma unroll
-            for (int u = 0; u < 8; u++) kw[c][u] = AT(kc[c], i + u);
-          }
+    for (int c = 0; c < 8; c++)
+      if (umask & (1u << c)) {
+        if (nc < 7) {
+          kk[nc] = kc[c];
+          cfk[nc] = cf[c];
+          cek[nc] = ce[c];
         }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          double acc = 0.0;
-#pragma unroll
-          for (int c = 0; c < 5; c++) acc = acc + kw[c][u] * cf[c];
-          const double v = (r == 0) ? yw[u] + temp * kw[0][u] * 233028180000.0 : yw[u] + temp * acc;
-          AT(w9, i + u) = v;
-          if (stash) AT(ys, i + u) = yw[u];
-          if (stash_k1) AT(ks, i + u) = kw[0][u];
-        }
+        nc++;
       }
+    if (on) {  // padding lanes of a short k group sit this out
+      const int r_u = r;
+      if (r_u == 0) i = combine_uniform<1, 8, true, false>(i, nmin, y, w9, kk, cfk, cek, temp, stash, stash_k1, ys, ks, errn, ynew);
+      else if (r_u == 7) i = combine_uniform<7, 4, false, true>(i, nmin, y, w9, kk, cfk, cek, temp, false, false, ys, ks, errn, ynew);
+      else if (nc == 2) i = combine_uniform<2, 8, false, false>(i, nmin, y, w9, kk, cfk, cek, temp, false, false, ys, ks, errn, ynew);
+      else if (nc == 3) i = combine_uniform<3, 8, false, false>(i, nmin, y, w9, kk, cfk, cek, temp, false, false, ys, ks, errn, ynew);
+      else if (nc == 4) i = combine_uniform<4, 8, false, false>(i, nmin, y, w9, kk, cfk, cek, temp, false, false, ys, ks, errn, ynew);
+      else if (nc == 5) i = combine_uniform<5, 8, false, false>(i, nmin, y, w9, kk, cfk, cek, temp, false, false, ys, ks, errn, ynew);
+      else if (nc == 6) i = combine_uniform<6, 4, false, false>(i, nmin, y, w9, kk, cfk, cek, temp, false, false, ys, ks, errn, ynew);
+    }
+    {  // first element the uniform loops did not cover (same for every lane)
+      const int ub = (umask & 0xe0u) ? 4 : 8;
+      i = 1 + (nmin / ub) * ub;
     }
   }
   for (; i <= nmax; i += 4) {
     // all loads of the batch first (up to 4 + 8 x 4 independent loads in flight), then the arithmetic, then the stores
     double yv[4], kv[8][4];
     bool p[4];
-    if (same_row && i + 3 <= nmin) {
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        p[u] = on;
-        yv[u] = 0.0;
-      }
-#pragma unroll
-      for (int c = 0; c < 8; c++)
-#pragma unroll
-        for (int u = 0; u < 4; u++) kv[c][u] = 0.0;
-      if (on) {  // padding lanes of a short k group sit this out
-#pragma unroll
-        for (int u = 0; u < 4; u++) yv[u] = AT(y, i + u);
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-          if (umask & (1u << c)) {
-#pragma unroll
-            for (int u = 0; u < 4; u++) kv[c][u] = AT(kc[c], i + u);
-          }
-        }
-      }
-    } else {
+    {
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         p[u] = i + u <= n;
@@ -811,6 +835,9 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
   // All warps of the CTA run the RHS evaluation together: the kernel's hot loop is ~8k straight-line
   // instructions (far beyond the 32 KB L1.5 instruction cache), so warps that reach derivs() at the same time
   // share one instruction stream from L2 instead of fetching it once per warp.
+#ifdef GC_PROFILE_PHASES
+  long long pw[5] = {0, 0, 0, 0, 0};
+#endif
   const bool align = __popc(__ballot_sync(0xffffffffu, have)) > 1;
   int wphase = 0;
   for (;; wphase = (wphase + 1) & 7) {
@@ -871,6 +898,10 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
     }
 #ifdef GC_PROFILE_PHASES
     __syncwarp();
+    if (tid == 0) {
+      long long t2 = clock64();
+      pw[0] += t_adv; pw[1] += t_comb; pw[2] += (t1 - t0) - t_adv - t_comb; pw[3] += t2 - t1; pw[4] += 1;
+    }
     if ((threadIdx.x & 31) == 0) {
       long long t2 = clock64();
       atomicAdd(&counters[5], (unsigned long long)t_adv);
@@ -880,6 +911,11 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
     }
 #endif
   }
+#ifdef GC_PROFILE_PHASES
+  if (tid == 0)
+    printf("[warp0] iterations %lld advance %.0f combine %.0f flush+loop %.0f derivs %.0f cycles/iteration\n", pw[4],
+           (double)pw[0] / pw[4], (double)pw[1] / pw[4], (double)pw[2] / pw[4], (double)pw[3] / pw[4]);
+#endif
   if (tid < nitems && !have) status[tid] = 0;
   if (have) {
     status[tid] = L.status;
