@@ -244,6 +244,31 @@ def main():
         tt = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt, dt_e2e = float(tt[0]), float(tt[1])
+    # ---------------- the same batch with desynchronised lanes (N = 1 only; reported next to `value`, not instead of it)
+    # Replicas march in lock step: all 32 lanes of a warp accept/reject the same steps.  A real MCMC batch holds
+    # different cosmologies whose adaptive step sequences differ (tools/gpu_hetero_probe.py draws one with the oracle
+    # as the host pre-stage).  The bench may not run the oracle on this arm, so it perturbs the one thing it can
+    # without a pre-stage: each replica's source k grid is scaled by a seeded random factor within +-2 %, which
+    # desynchronises the lanes the same way (measured within 4 % of the distinct-cosmology batch, profiles/README.md).
+    desync = None
+    if world == 1:
+        rng = np.random.default_rng(20250101)
+        jm = [fixture.copy() for _ in range(B)]
+        for m in jm[1:]:
+            m.d["k"] = m.d["k"] * (1 + 0.02 * rng.uniform(-1, 1))
+        g.set_models(jm)
+        step_resident()
+        barrier()
+        t2 = time.perf_counter()
+        nd = max(1, min(2, args.steps))
+        for _ in range(nd):
+            step_resident()
+        barrier()
+        dt_d = time.perf_counter() - t2
+        _, cl0 = g.Cls(0)
+        desync = {"value": B * nd / dt_d, "unit": UNIT, "steps": nd, "ms_per_step": 1e3 * dt_d / nd,
+                  "evolve_ms": g.timings()["evolve"],
+                  "workload": "same batch, source k grids of replicas 1..B-1 scaled by seeded random factors within +-2 %"}
     # parity guard inside the bench: the last model's C_l against the committed golden
     gold = np.load(os.path.join(GOLD, "config2_golden.npz"))
     cl_err = float(np.max(np.abs(out[-1] / gold["Cl"] - 1)))
@@ -269,7 +294,7 @@ def main():
             "config": {"workload": "BASELINE configs[1]: Galileon scalar C_l lmax=2500 (camb/params.ini accuracy), batch of "
                                    "%d parameter points per GPU (replicas of tests/golden/config2_tables.npz)" % B,
                        "batch_per_gpu": B, "l2_note": "inputs larger than L2: per-step working set = %.0f MB of model tables + %.0f MB of ODE "
-                       "workspace vs 126 MB L2" % (B * fixture.nbytes() / 1e6, B * 197 * 9.1e-3), "parallelism": "parameter points sharded across ranks; NCCL all-gather of C_l"},
+                       "workspace vs 126 MB L2" % (B * fixture.nbytes() / 1e6, B * 197 * 10.3e-3), "parallelism": "parameter points sharded across ranks; NCCL all-gather of C_l"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * fixture.nbytes()),
                     "d2h_bytes_per_step": int(out.nbytes)},
             "gpu_launches": int(args.steps * 6),  # evolve, spline_k, zero_delta, los, cl, cl_interp per step
@@ -277,8 +302,8 @@ def main():
             "roofline": {"kernel": "evolve_sources_kernel", "bound": "fp64", "achieved": flop / t_ev / 1e12, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": flop / t_ev / 1e12 / fp64_peak,
                          "peak_source": "measured: galcamb_fp64_peak_ DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure; nominal 37.2)",
-                         "traffic": 5.19e9 * B, "traffic_source": "dram__bytes.sum of the ncu capture profiles/r1_evolve_b448_final_sections "
-                         "(768 GB/s x 3.025 s / 448 spectra = 5.19 GB per spectrum), scaled to this batch; bytes, per launch",
+                         "traffic": 3.38e9 * B, "traffic_source": "DRAM bytes of the ncu capture profiles/r1b_evolve_b256_sections.txt "
+                         "(441.09 GB/s x 1.96 s / 256 spectra = 3.38 GB per spectrum), scaled to this batch; bytes, per launch",
                          "share_of_step": ev["evolve"] / (ev["evolve"] + ev["spline_k"] + ev["los"] + ev["cls"]),
                          "flop_per_spectrum": meta["flop_ode"], "ms_per_launch": 1e3 * t_ev},
             "roofline_los": {"kernel": "los_kernel", "bound": "hbm", "achieved": meta["bytes_los_operand"] * B / t_los / 1e9,
@@ -290,6 +315,8 @@ def main():
             "counters_last_step": counters,
             "parity": {"cl_max_rel_err_vs_golden": cl_err, "tolerance": 1e-5},
         }
+        if desync is not None:
+            line["desync"] = desync
         if world == 1 and not args.no_cpu:
             cpu_reference_rate(2)  # warm-up + layout choice
             r, cores, lanes, tpm, dtc = cpu_reference_rate(max(8, 2 * (os.cpu_count() or 8)))
