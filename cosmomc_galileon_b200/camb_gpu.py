@@ -166,6 +166,8 @@ def load_library():
         L.galcamb_get_status_.argtypes = [C.POINTER(_I), C.POINTER(_I)]
         L.galcamb_batch_cls_.argtypes = [C.POINTER(CModel), C.POINTER(_I), C.c_void_p]
         L.galcamb_batch_lensed_cls_.argtypes = [C.POINTER(CModel), C.POINTER(_I), C.c_void_p, C.POINTER(_I), C.c_void_p]
+        L.galcamb_set_primordial_.argtypes = [C.POINTER(_I)] + [C.POINTER(_D)] * 5
+        L.galcamb_transfers_to_powers_.argtypes = [C.POINTER(_I)]
         L.galcamb_get_timings_.argtypes = [C.c_void_p]
         L.galcamb_get_counters_.argtypes = [C.c_void_p]
         L.galcamb_get_evolve_stats_.argtypes = [C.c_void_p]
@@ -240,6 +242,18 @@ class GalCamb:
     # ClTransferToCl, camb/cmbmain.f90:293
     def ClTransferToCl(self):
         self._chk(self.L.galcamb_scalar_cls_())
+
+    # CAMB_TransfersToPowers, camb/camb.f90:87: fast-parameter update on resident transfer functions
+    def set_primordial(self, slot, ScalarPowerAmp, an, n_run=0.0, n_runrun=0.0, k_0_scalar=0.05):
+        self._chk(self.L.galcamb_set_primordial_(C.byref(_I(slot)), C.byref(_D(ScalarPowerAmp)), C.byref(_D(an)),
+                                                 C.byref(_D(n_run)), C.byref(_D(n_runrun)), C.byref(_D(k_0_scalar))))
+        d = self.models[slot].d
+        d["ScalarPowerAmp"], d["an"], d["n_run"], d["n_runrun"], d["k_0_scalar"] = ScalarPowerAmp, an, n_run, n_runrun, k_0_scalar
+
+    def TransfersToPowers(self, do_lensing=False):
+        rc = self.L.galcamb_transfers_to_powers_(C.byref(_I(int(do_lensing))))
+        if rc != 8:
+            self._chk(rc)
 
     # lens_Cls, camb/lensing.f90:78 (after ClTransferToCl on DoLensing models)
     def lens_Cls(self):

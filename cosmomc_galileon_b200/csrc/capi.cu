@@ -730,6 +730,27 @@ int galcamb_get_lensed_cls_(const int* slot, int* lmax_lensed, double* Cl_lensed
   return 0;
 }
 
+// CAMB_TransfersToPowers, camb/camb.f90:87-102 (the fast-parameter path of source/Calculator_CAMB.f90:258): new
+// primordial parameters for a slot whose Delta_p_l_k is still on the device, then ClTransferToCl (+ lens_Cls) only.
+int galcamb_set_primordial_(const int* slot, const double* ScalarPowerAmp, const double* an, const double* n_run,
+                            const double* n_runrun, const double* k_0_scalar) {
+  if (*slot < 0 || *slot >= (int)g.slots.size() || !g.slots[*slot].set) return fail(5, "bad slot");
+  if (!(*ScalarPowerAmp > 0) || !(*k_0_scalar > 0)) return fail(3, "bad primordial power spectrum");  // error_inital_power
+  DevModel& D = g.slots[*slot].host;
+  D.ScalarPowerAmp = *ScalarPowerAmp;
+  D.an = *an;
+  D.n_run = *n_run;
+  D.n_runrun = *n_runrun;
+  D.k_0_scalar = *k_0_scalar;
+  return 0;
+}
+
+int galcamb_transfers_to_powers_(const int* do_lensing) {
+  if (int rc = galcamb_scalar_cls_()) return rc;
+  if (*do_lensing) return galcamb_lens_cls_();
+  return 0;
+}
+
 int galcamb_get_sources_(const int* slot, double* Src) {
   if (*slot < 0 || *slot >= (int)g.slots.size() || !g.slots[*slot].set) return fail(5, "bad slot");
   const DevModel& D = g.slots[*slot].host;

@@ -125,6 +125,12 @@ int galcamb_get_status_(const int* slot, int* status);           /* per-slot CAM
  * Returns 8 (error_norm_lensing, camb/constants.f90:80) if a slot fails the normalisation check (:230-235).
  *   Cl_lensed(lmin:lmax_lensed, 1:4) = TT, EE, BB, TE laid out [type][l-2] */
 int galcamb_lens_cls_(void);
+/* CAMB_TransfersToPowers, camb/camb.f90:87-102 -- what CosmoMC calls when only fast parameters changed
+ * (source/Calculator_CAMB.f90:258): new InitPower values for a slot whose Delta_p_l_k is still resident, then
+ * ClTransferToCl (and lens_Cls if *do_lensing) for the batch.  No ODE, no line-of-sight work. */
+int galcamb_set_primordial_(const int* slot, const double* ScalarPowerAmp, const double* an, const double* n_run,
+                            const double* n_runrun, const double* k_0_scalar);
+int galcamb_transfers_to_powers_(const int* do_lensing);
 int galcamb_get_lensed_cls_(const int* slot, int* lmax_lensed, double* Cl_lensed /* may be NULL */);
 
 /* one call for a whole batch: set models, run stages 1-4, return Cl(lmin:lmax,3) per model contiguous */

@@ -96,6 +96,16 @@ def test_three_source_variants_against_oracle(gpu, kw, lmax):
     check_lensed(lensed_b[0], o.Cl_lensed(), TOL_CL)
     assert np.max(np.abs(cl_b[0, :2] / o.Cl()[:2] - 1)) < TOL_CL
     assert gpu.status(0) == 0 and gpu.status(1) == 4 and np.all(np.isnan(lensed_b[1]))
+    # fast-parameter update (CAMB_TransfersToPowers, camb/camb.f90:87): new A_s, n_s on the resident transfer functions
+    o.set(ScalarPowerAmp=2.3e-9, an=0.95)
+    o.stage("cls", "lensing")
+    gpu.set_primordial(0, 2.3e-9, 0.95)
+    n_before = gpu.evolve_stats()["rhs_executed"]
+    gpu.TransfersToPowers(do_lensing=True)
+    assert gpu.evolve_stats()["rhs_executed"] == n_before  # no ODE work
+    _, cl2 = gpu.Cls(0)
+    assert np.max(np.abs(cl2[:2] / o.Cl()[:2] - 1)) < TOL_CL
+    check_lensed(gpu.Cl_lensed(0), o.Cl_lensed(), TOL_CL)
 
 
 def check_lensed(L, Lo, tol):
@@ -212,6 +222,39 @@ def test_heterogeneous_batch(gpu):
         assert np.max(np.abs(out[i] / o.Cl()[:3] - 1)) < TOL_CL
         assert relmax(gpu.Src(i), o.Src()) < TOL_TRANSFER
         assert relmax(gpu.Delta_p_l_k(i), o.Delta()) < TOL_TRANSFER
+
+
+def test_distinct_cosmology_batch(gpu):
+    """BASELINE configs[3] in small: 48 DIFFERENT parameter points drawn like SURVEY.md 8d's config 4 (seeded Gaussians
+    around the config-2 point, stability rejects redrawn).  Their k grids, switch times and adaptive step sequences
+    differ, so the lanes of a warp fall out of step: this is the test of the stage alignment, the shared output
+    derivative and the deferred output evaluation of K1.  Every 6th point is checked against its own oracle run."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLD), "..", "tools"))
+    from gpu_hetero_probe import draw, prestage
+    from oracle_py import Oracle
+    rng = np.random.default_rng(7)
+    tabs, pars = [], []
+    while len(tabs) < 48:
+        P = draw(rng, 1.0)
+        t = prestage(P)
+        if t is not None:
+            tabs.append(t)
+            pars.append(P)
+    gpu.InitSpherBessels(tabs[0].ls, 6251, 1.0)
+    out = gpu.batch_cls(tabs)
+    assert all(gpu.status(i) == 0 for i in range(48))
+    st = gpu.evolve_stats()
+    assert st["outputs_from_k1"] > 0.9 * gpu.counters()["n_out"]  # nearly every output shares the next step's k1
+    n_alg = 0.0
+    for i in range(0, 48, 6):
+        o = Oracle(**pars[i])
+        o.run()
+        assert np.max(np.abs(out[i] / o.Cl()[:3] - 1)[:2]) < TOL_CL
+        assert relmax(out[i][2], o.Cl()[2]) < TOL_CL
+        assert relmax(gpu.Src(i), o.Src()) < TOL_TRANSFER
+        n_alg += o.get("n_derivs")
+    assert n_alg > 0
 
 
 def test_massless_neutrino_model(gpu):
