@@ -6,17 +6,19 @@
 //
 // Execution model (DESIGN.md "K1"): one lane per (k, cosmology) work item, FP64 throughout.  Each lane runs the
 // reference's control flow (output-time loop, approximation switches, adaptive step accept/reject) as an explicit
-// state machine that stops whenever it needs a right-hand-side evaluation; the warp then executes ONE converged
-// call of derivs() for all of its lanes.  Lanes of a warp therefore share the ~2 kFLOP RHS instruction stream
-// even when they sit in different Runge-Kutta stages, at different step sizes or in different output intervals;
-// only the short bookkeeping between evaluations diverges.
+// scalar state machine (advance) that stops whenever it needs one of three vector operations, which the warp then
+// executes as ONE converged call for all of its lanes: the right-hand side (derivs), a stage combination of the
+// Runge-Kutta tableau (combine) or the source evaluation of an output time (flush_output).  Lanes of different
+// cosmologies need different numbers of steps; they are kept in the same Runge-Kutta stage by letting a lane start a
+// trial step only every 8th round (PH_DV_LOOP), so that only the short scalar bookkeeping diverges.
 #include <algorithm>
 #include <cstddef>
 #include <cstdio>
 
 #include "evolve_device.cuh"
 
-// 4 warps per CTA, 3 CTAs per SM (168 registers); the warps of a CTA run derivs() in lock-step (see the main loop)
+// batch mode: 4 warps per CTA, 2 CTAs per SM (255 registers, 113 KB of lane records each); the warps of a CTA run
+// derivs() in lock-step (see the main loop)
 #ifndef GC_EVOLVE_THREADS
 #define GC_EVOLVE_THREADS 128
 #endif
