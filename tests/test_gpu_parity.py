@@ -108,6 +108,29 @@ def test_three_source_variants_against_oracle(gpu, kw, lmax):
     check_lensed(gpu.Cl_lensed(0), o.Cl_lensed(), TOL_CL)
 
 
+def test_config3_lensed_accuracyboost2_lmax5000(gpu):
+    """BASELINE configs[2] at full size: Galileon lensed C_l, AccuracyBoost = 2, lmax = 5000 (557 source k, 1238 output
+    times, 10814 integration k, 135 multipoles, 3 sources, every k integrated to tau0), all five stages."""
+    from oracle_py import Oracle
+    from tables_from_oracle import tables_from_oracle
+    P = dict(GAL, DoLensing=1, AccuracyBoost=2)
+    o = Oracle(lmax=5000, **P)
+    o.run()
+    o.stage("lensing")
+    t = tables_from_oracle(o, P, lmax=5000)
+    run_gpu(gpu, t)
+    gpu.lens_Cls()
+    S, So = gpu.Src(), o.Src()
+    for s in range(3):
+        assert relmax(S[:, s], So[:, s]) < TOL_TRANSFER
+    assert relmax(gpu.Delta_p_l_k(), o.Delta()) < TOL_TRANSFER
+    icl, cl = gpu.Cls()
+    assert np.max(np.abs(cl[:4] / o.Cl()[:4] - 1)) < TOL_CL
+    check_lensed(gpu.Cl_lensed(), o.Cl_lensed(), TOL_CL)
+    assert gpu.Cl_lensed().shape[1] == 4899
+    print("config 3 stage ms:", gpu.timings())
+
+
 def check_lensed(L, Lo, tol):
     assert L.shape == Lo.shape
     for t_ in (0, 1, 2):  # TT, EE, BB are positive
