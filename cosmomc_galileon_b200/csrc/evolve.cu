@@ -310,6 +310,87 @@ __device__ __forceinline__ void combine(Lane& L) {
   L.crow = -1;
 }
 
+// combine() for warps that hold few work items (up to 16 models in flight: one k group = the low lanes of a warp, the
+// rest padding): the idle lanes help.  The warp splits into groups of `gsz` lanes {o, o + nown, o + 2 nown, ...} around
+// each owner lane o < nown; every lane of a group reads the owner's lane record from shared memory and forms the
+// elements i = sub + 1, sub + 1 + gsz, ... of the owner's stage input -- each element by one lane, in the same
+// left-to-right order, so the result is bit-identical to combine()'s.  Single model: 110 elements in one batch of 4
+// per lane instead of 28 sequential batches on one lane.
+__device__ __forceinline__ void combine_group(unsigned char* smem_base, int nown) {
+  const int lane = threadIdx.x & 31;
+  const int owner = lane % nown, sub = lane / nown, gsz = 32 / nown;
+  Lane& O = *reinterpret_cast<Lane*>(smem_base + (size_t)((threadIdx.x & ~31) + owner) * GC_LANE_STRIDE);
+  const bool on = O.crow >= 0;
+  const int r = on ? O.crow : 0;
+  const int n = on ? O.e.neq : 0;
+  const unsigned cmask = on ? c_rowmask[r] : 0u;
+  const bool fin = on && r == 7;
+  const double* __restrict__ y = col(O, 0);
+  double* __restrict__ w9 = col(O, 9);
+  const double temp = O.htrial / 1398169080000.0;
+  const bool stash = on && O.out_pending && !O.out_stashed;
+  const bool stash_k1 = stash && O.stash_k1;
+  double* __restrict__ ys = O.ws + (size_t)10 * O.NV * GC_LANES;
+  double* __restrict__ ks = O.ws + (size_t)11 * O.NV * GC_LANES;
+  const int nmax = __reduce_max_sync(0xffffffffu, n);
+  double errn = 0.0, ynew = 0.0;
+  for (int i0 = 1 + sub; i0 <= nmax; i0 += 4 * gsz) {
+    double yv[4], kv[8][4];
+    bool p[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      p[u] = i0 + u * gsz <= n;
+      yv[u] = p[u] ? AT(y, i0 + u * gsz) : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const bool mine = (cmask >> c) & 1u;
+      const double* kcol = O.ws + (size_t)(c + 1) * O.NV * GC_LANES;
+#pragma unroll
+      for (int u = 0; u < 4; u++) kv[c][u] = (mine && p[u]) ? AT(kcol, i0 + u * gsz) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (p[u]) {
+        const int i = i0 + u * gsz;
+        double a1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) a1 = a1 + kv[c][u] * c_row[r][c];
+        const double v = (r == 0) ? yv[u] + temp * kv[0][u] * 233028180000.0 : yv[u] + temp * a1;
+        AT(w9, i) = v;
+        if (stash) AT(ys, i) = yv[u];
+        if (stash_k1) AT(ks, i) = kv[0][u];
+        if (fin) {
+          double a2 = 0.0;
+#pragma unroll
+          for (int c = 0; c < 8; c++) a2 = a2 + kv[c][u] * c_err[c];
+          const double w2 = a2 / 1398169080000.0;
+          errn = fmax(errn, fabs(w2) / fmax(1.0, fabs(yv[u])));
+          ynew = fmax(ynew, fabs(v));
+        }
+      }
+    }
+  }
+  // max over the lanes of a group (they differ in the bits above log2(nown))
+  for (int o = nown; o < 32; o <<= 1) {
+    errn = fmax(errn, __shfl_xor_sync(0xffffffffu, errn, o));
+    ynew = fmax(ynew, __shfl_xor_sync(0xffffffffu, ynew, o));
+  }
+  __syncwarp();  // every helper has read the owner's record before the owner changes it
+  if (sub == 0 && on) {
+    if (fin) {
+      O.errn = errn;
+      O.ynorm_new = ynew;
+    }
+    if (stash) {
+      O.out_stashed = true;
+      O.stash_k1 = false;
+    }
+    O.crow = -1;
+  }
+  __syncwarp();
+}
+
 // Deferred output_sources(): called from the main loop when ANY lane of the warp must have its pending output out
 // of the way (it reached its next output time, a switch or the end); every lane with a pending output joins, so a
 // warp whose lanes reach their output times in different iterations still runs the ~2 kFLOP source evaluation about
@@ -840,7 +921,14 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
 #ifdef GC_PROFILE_PHASES
   long long pw[5] = {0, 0, 0, 0, 0};
 #endif
-  const bool align = __popc(__ballot_sync(0xffffffffu, have)) > 1;
+  const unsigned have_mask = __ballot_sync(0xffffffffu, have);
+  const bool align = __popc(have_mask) > 1;
+  // few items in this warp (they are its low lanes): the padding lanes help in combine_group()
+  int nown = 0;
+  if (have_mask && __popc(have_mask) <= 16 && have_mask == (1u << __popc(have_mask)) - 1u) {
+    nown = 1;
+    while (nown < __popc(have_mask)) nown <<= 1;
+  }
   int wphase = 0;
   for (;; wphase = (wphase + 1) & 7) {
     // control flow up to the next RHS request.  A lane normally needs one pass: advance() leaves a stage
@@ -872,7 +960,10 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
       long long tc = clock64();
       t_flush += tc - tb;
 #endif
-      if (__any_sync(0xffffffffu, L.crow >= 0)) combine(L);
+      if (__any_sync(0xffffffffu, L.crow >= 0)) {
+        if (nown) combine_group(gc_smem_raw, nown);
+        else combine(L);
+      }
 #ifdef GC_PROFILE_PHASES
       __syncwarp();
       t_comb += clock64() - tc;
