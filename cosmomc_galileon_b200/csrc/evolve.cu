@@ -317,6 +317,7 @@ __device__ __forceinline__ void combine(Lane& L) {
 // left-to-right order, so the result is bit-identical to combine()'s.  Single model: 110 elements in one batch of 4
 // per lane instead of 28 sequential batches on one lane.
 __device__ __forceinline__ void combine_group(unsigned char* smem_base, int nown) {
+  __syncwarp();  // the owners' records were written by their own lanes (advance)
   const int lane = threadIdx.x & 31;
   const int owner = lane % nown, sub = lane / nown, gsz = 32 / nown;
   Lane& O = *reinterpret_cast<Lane*>(smem_base + (size_t)((threadIdx.x & ~31) + owner) * GC_LANE_STRIDE);
