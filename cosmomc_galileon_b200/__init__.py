@@ -5,5 +5,6 @@ include/galcamb.h.  The product is libgalcamb_b200.so; this package only loads i
 shards batches across ranks.  There is no CPU fallback: importing works anywhere, computing needs a B200.
 """
 from .camb_gpu import GalCamb, ModelTables, lib_path, load_library  # noqa: F401
+from .cl_files import write_lensed_cls, write_scalar_cls  # noqa: F401
 
-__all__ = ["GalCamb", "ModelTables", "lib_path", "load_library"]
+__all__ = ["GalCamb", "ModelTables", "lib_path", "load_library", "write_scalar_cls", "write_lensed_cls"]
