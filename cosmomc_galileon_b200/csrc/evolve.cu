@@ -137,6 +137,19 @@ __constant__ unsigned c_rowmask[8] = {0x01, 0x03, 0x07, 0x0f, 0x1f, 0x1f, 0x5f, 
 // rows that read up to five columns, 4 for the last two).  Runs over the full batches below nend; the generic loop of combine() finishes the tail.
 //   ROW0: w9 = y + (temp*w1)*c with the reference's association (camb/subroutines.f90:930), plus the copies a pending
 //         output needs;  FIN: trial solution + error vector of the last row (:995-1019).
+// loads of the derivative columns in the stage combinations: streamed once per row, never reused from L1 -> keep them
+// out of it (cache-global); in the last row they are dead afterwards (cache-streaming = evict first)
+#ifndef GC_LDK_MODE
+#define GC_LDK_MODE 1
+#endif
+#if GC_LDK_MODE == 1
+#define GC_LDK(fin, p) ((fin) ? __ldcs(p) : __ldcg(p))
+#elif GC_LDK_MODE == 2
+#define GC_LDK(fin, p) __ldcg(p)
+#else
+#define GC_LDK(fin, p) (*(p))
+#endif
+
 template <int NC, int U, bool ROW0, bool FIN>
 __device__ __forceinline__ int combine_uniform(int i, int nend, const double* __restrict__ y, double* __restrict__ w9,
                                                const double* const* kc, const double* cf, const double* ce, double temp,
@@ -150,7 +163,7 @@ __device__ __forceinline__ int combine_uniform(int i, int nend, const double* __
 #pragma unroll
     for (int c = 0; c < NC; c++)
 #pragma unroll
-      for (int u = 0; u < U; u++) kv[c][u] = AT(kc[c], i + u);
+      for (int u = 0; u < U; u++) kv[c][u] = GC_LDK(FIN, &AT(kc[c], i + u));
 #pragma unroll
     for (int u = 0; u < U; u++) {
       double v;
@@ -262,7 +275,7 @@ __device__ __forceinline__ void combine(Lane& L) {
         if (umask & (1u << c)) {
           const bool mine = (cmask >> c) & 1u;
 #pragma unroll
-          for (int u = 0; u < 4; u++) kv[c][u] = (mine && p[u]) ? AT(kc[c], i + u) : 0.0;
+          for (int u = 0; u < 4; u++) kv[c][u] = (mine && p[u]) ? GC_LDK(false, &AT(kc[c], i + u)) : 0.0;
         } else {
 #pragma unroll
           for (int u = 0; u < 4; u++) kv[c][u] = 0.0;
@@ -348,7 +361,7 @@ __device__ __forceinline__ void combine_group(unsigned char* smem_base, int nown
       const bool mine = (cmask >> c) & 1u;
       const double* kcol = O.ws + (size_t)(c + 1) * O.NV * GC_LANES;
 #pragma unroll
-      for (int u = 0; u < 4; u++) kv[c][u] = (mine && p[u]) ? AT(kcol, i0 + u * gsz) : 0.0;
+      for (int u = 0; u < 4; u++) kv[c][u] = (mine && p[u]) ? GC_LDK(false, &AT(kcol, i0 + u * gsz)) : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
