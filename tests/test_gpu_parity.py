@@ -286,6 +286,23 @@ def test_distinct_cosmology_batch(gpu):
     assert n_alg > 0
 
 
+def test_distinct_cosmology_batch_in_batch_mode():
+    """The same kind of batch through the lock-step launch shape (4-warp CTAs, all columns in global memory), which the
+    launcher only picks above ~800 models: forced here with GALCAMB_LATENCY_ITEMS=0 in a fresh process (the knob is read
+    once per process).  40 distinct points = one full warp and one warp of 8 items (cooperative combine) per k index."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GALCAMB_LATENCY_ITEMS="0")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_hetero_probe.py"), "40"], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(re.findall(r"failed slots 0;", r.stdout)) == 2, r.stdout
+    m = re.search(r"vs the oracle: ([0-9.e+-]+)", r.stdout)
+    assert m and float(m.group(1)) < TOL_CL, r.stdout
+
+
 def test_massless_neutrino_model(gpu):
     """No massive eigenstate (omnuh2 = 0 -> Num_Nu_massive = 0, camb/modules.f90:307-316): the neutrino blocks of the
     state vector and the table lookups disappear."""
