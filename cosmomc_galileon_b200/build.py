@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libgalcamb_b200.so")
-SOURCES = ["evolve.cu", "los.cu", "lensing.cu", "capi.cu", "fp64_peak.cu"]
+SOURCES = ["evolve.cu", "los.cu", "lensing.cu", "capi.cu", "fp64_peak.cu", "galileon_host.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FMAD = os.environ.get("GALCAMB_FMAD", "true")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=" + FMAD, "-std=c++17", "-Xcompiler",
@@ -33,6 +33,7 @@ def build(verbose=False, force=False):
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "galcamb.h"))
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "galileon_abi.h"))
     jobs = []
     for s in SOURCES:
         src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s.replace(".cu", ".o"))

@@ -16,6 +16,8 @@
 #include "galileon_fast.cuh"
 #include "model.h"
 
+// functions shared with the host-side galileon.cc replacement (csrc/galileon_host.cu)
+#define GC_HD __host__ __device__
 #define GC_LANES 32
 #define GC_NCOL 12  // column 0 = y, columns 1..9 = dverk w(:,1..9), 10 = y of a pending output, 11 = its y'
 
@@ -48,7 +50,7 @@ __device__ __forceinline__ double polfack(const EV& e, int l) { return c_polfac[
 __device__ __forceinline__ long nintd(double x) { return lround(x); }
 
 // ---------------------------------------------------------------- table lookups
-__device__ __forceinline__ double herm(double f0, double d0, double f1, double d1, double d) {
+GC_HD __forceinline__ double herm(double f0, double d0, double f1, double d1, double d) {
   return f0 + d * (d0 + d * (3 * (f1 - f0) - 2 * d0 - d1 + d * (d0 + d1 + 2 * (f0 - f1))));
 }
 
@@ -100,7 +102,7 @@ __device__ inline double Thermo_OpacityToTime(const DevModel& M, double opacity)
 
 // nu_tab rows: {r1, dr1, p1, dp1, ddr1, ddp1}
 // camb/modules.f90:1721-1754
-__device__ inline void Nu_background(const DevModel& M, double am, double& rhonu, double& pnu) {
+GC_HD inline void Nu_background(const DevModel& M, double am, double& rhonu, double& pnu) {
   if (am <= GC_AM_MINP) {
     rhonu = 1.0 + GC_NU_CONST2 * am * am;
     pnu = (2 - rhonu) / 3.0;
@@ -120,7 +122,7 @@ __device__ inline void Nu_background(const DevModel& M, double am, double& rhonu
 }
 
 // camb/modules.f90:1790-1817
-__device__ inline double Nu_drho(const DevModel& M, double am, double adotoa, double rhonu) {
+GC_HD inline double Nu_drho(const DevModel& M, double am, double adotoa, double rhonu) {
   if (am < GC_AM_MINP) return 2 * GC_NU_CONST2 * am * am * adotoa;
   if (am > GC_AM_MAXP) return 3 / (2 * GC_NU_CONST) * (GC_ZETA3 * am - (15 * GC_ZETA5) / 2 / am) * adotoa;
   double d = log(am * 100.0) * M.inv_dlnam + 1.0;
@@ -132,7 +134,7 @@ __device__ inline double Nu_drho(const DevModel& M, double am, double adotoa, do
 }
 
 // camb/modules.f90:1821-1850
-__device__ inline double Nu_dp(const DevModel& M, double am, double adotoa, double pnu) {
+GC_HD inline double Nu_dp(const DevModel& M, double am, double adotoa, double pnu) {
   if (am < GC_AM_MINP) return 2 * adotoa * (1.0 - GC_NU_CONST2 * am * am) / 3.0 - 4.0 / 3.0 * adotoa;
   if (am > GC_AM_MAXP)
     return -900.0 / 120.0 / GC_NU_CONST * (GC_ZETA5 - 189.0 / 4 * GC_ZETA7 / (am * am)) * adotoa / am;
@@ -257,7 +259,7 @@ struct GalC {
 };
 
 // camb/galileon.cc:746-787
-__device__ inline void gal_GetdHdX(const DevModel& M, double a, double hc, double xc, const double* pnu, double& dh,
+GC_HD inline void gal_GetdHdX(const DevModel& M, double a, double hc, double xc, const double* pnu, double& dh,
                                    double& dx) {
   const double c2 = M.c2, c3 = M.c3, c4 = M.c4, c5 = M.c5, cG = M.cG, h0 = M.h0, orad = M.orad;
   const double a2 = a * a;
@@ -277,7 +279,7 @@ __device__ inline void gal_GetdHdX(const DevModel& M, double a, double hc, doubl
 }
 
 // camb/galileon.cc:809-829
-__device__ inline double gal_grhogal(const DevModel& M, double a, double hc, double xc) {
+GC_HD inline double gal_grhogal(const DevModel& M, double a, double hc, double xc) {
   if (!(a >= 9.99999e-7)) return 0;
   const double c2 = M.c2, c3 = M.c3, c4 = M.c4, c5 = M.c5, cG = M.cG, h0 = M.h0;
   const double xgal2 = xc * xc, xgal3 = xgal2 * xc, xgal4 = xgal2 * xgal2, xgal5 = xgal2 * xgal3;
@@ -288,7 +290,7 @@ __device__ inline double gal_grhogal(const DevModel& M, double a, double hc, dou
 }
 
 // camb/galileon.cc:831-850
-__device__ inline double gal_gpresgal(const DevModel& M, double a, double hc, double xc, double dh, double dx) {
+GC_HD inline double gal_gpresgal(const DevModel& M, double a, double hc, double xc, double dh, double dx) {
   if (!(a >= 9.99999e-7)) return 0;
   const double c2 = M.c2, c3 = M.c3, c4 = M.c4, c5 = M.c5, cG = M.cG, h0 = M.h0;
   const double xgal2 = xc * xc, xgal4 = xgal2 * xgal2;
@@ -301,7 +303,7 @@ __device__ inline double gal_gpresgal(const DevModel& M, double a, double hc, do
 }
 
 // camb/galileon.cc:852-895
-__device__ inline double gal_Chigal(const DevModel& M, double a, double hc, double xc, double dgrho, double eta,
+GC_HD inline double gal_Chigal(const DevModel& M, double a, double hc, double xc, double dgrho, double eta,
                                     double dphi, double dphip, double k) {
   if (!(a >= 9.99999e-7)) return 0;
   const double c2 = M.c2, c3 = M.c3, c4 = M.c4, c5 = M.c5, cG = M.cG, h0 = M.h0;
@@ -320,7 +322,7 @@ __device__ inline double gal_Chigal(const DevModel& M, double a, double hc, doub
 }
 
 // camb/galileon.cc:897-936
-__device__ inline double gal_qgal(const DevModel& M, double a, double hc, double xc, double dgq, double eta, double dphi,
+GC_HD inline double gal_qgal(const DevModel& M, double a, double hc, double xc, double dgq, double eta, double dphi,
                                   double dphip, double k) {
   if (!(a >= 9.99999e-7)) return 0;
   const double c2 = M.c2, c3 = M.c3, c4 = M.c4, c5 = M.c5, cG = M.cG, h0 = M.h0;
@@ -337,7 +339,7 @@ __device__ inline double gal_qgal(const DevModel& M, double a, double hc, double
 }
 
 // camb/galileon.cc:938-985
-__device__ inline double gal_Pigal(const DevModel& M, double a, double hc, double xc, double dh, double dx, double dgrho,
+GC_HD inline double gal_Pigal(const DevModel& M, double a, double hc, double xc, double dh, double dx, double dgrho,
                                    double dgq, double dgpi, double eta, double dphi, double k) {
   if (!(a >= 9.99999e-7)) return 0;
   const double c4 = M.c4, c5 = M.c5, cG = M.cG, h0 = M.h0;
@@ -362,7 +364,7 @@ __device__ inline double gal_Pigal(const DevModel& M, double a, double hc, doubl
                     (alpha_sig + alpha_sigprime) * k * eta);
 }
 // camb/galileon.cc:987-1082
-__device__ inline double gal_dphisecond(const DevModel& M, double a, double hc, double xc, double dh, double dx,
+GC_HD inline double gal_dphisecond(const DevModel& M, double a, double hc, double xc, double dh, double dx,
                                         double dgrho, double dgq, double eta, double dphi, double dphip, double k,
                                         double deltafprime) {
   if (!(a >= 9.99999e-7)) return 0;
@@ -445,7 +447,7 @@ __device__ inline double gal_dphisecond(const DevModel& M, double a, double hc, 
 }
 
 // camb/galileon.cc:1084-1174
-__device__ inline double gal_pigalprime(const DevModel& M, double a, double hc, double xc, double dh, double dx,
+GC_HD inline double gal_pigalprime(const DevModel& M, double a, double hc, double xc, double dh, double dx,
                                         double dgrho, double dgq, double dgpi, double pidot, double eta, double dphi,
                                         double dphip, double k, double grho, double gpres, const double* pnu) {
   if (!(a >= 9.99999e-7)) return 0;
@@ -1108,7 +1110,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
 // ---------------------------------------------------------------- output
 // camb/equations_galileon.f90:1256-1576, everything after the derivs call at :1297.
 // ts = this output time's row {tau, dtau, vis, dvis, ddvis, expmmu, opac, dopac}.
-__device__ __noinline__ void output_sources(const DevModel* __restrict__ Mp, const EV* __restrict__ ep,
+static __device__ __noinline__ void output_sources(const DevModel* __restrict__ Mp, const EV* __restrict__ ep,
                                             const double* __restrict__ y, const double* __restrict__ yprime,
                                             const double* __restrict__ ts, double tau, double* __restrict__ sources) {
   const DevModel& M = *Mp;

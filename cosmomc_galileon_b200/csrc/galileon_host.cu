@@ -1,0 +1,405 @@
+// Host-side replacement of camb/galileon.cc -- the reference's own C ABI (camb/interface.f90:7-92): background
+// integration of the Galileon field (arrays_), table accessors (GetX_, GetH_), and the closed-form background /
+// perturbation terms the Fortran equations call per RHS evaluation.  First "next" row of SURVEY.md section 8f (the
+// Galileon part of the host pre-stage).  Differences from the reference, all at the boundary:
+//   * no GSL: the Fehlberg 4(5) stepper with gsl_odeiv_control_y_new(1e-18, 1e-16) semantics and the natural cubic
+//     spline (= gsl_interp_cspline) are written out here (camb/galileon.cc:344-363, :666-682);
+//   * no call-backs into Fortran (MassiveNu::Nu_rho/Nu_background/Nu_dp, camb/galileon.cc:96-99): the host passes
+//     its massive-neutrino tables once with galileon_set_nu_tables_();
+//   * errors come back as the integer status of arrays_ (camb/equations_galileon.f90:97-100); an out-of-range `a` in
+//     GetX_/GetH_ returns NaN instead of exit() (camb/galileon.cc:698-701).
+// The closed forms are the same functions the device code evaluates (evolve_device.cuh, __host__ __device__).
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "evolve_device.cuh"
+#include "../../include/galileon_abi.h"
+
+namespace {
+
+using gc::Nu_background;
+
+struct HostGal {
+  DevModel M{};  // constants c2..c5, cG, h0, orad, n_eig, grhormass, nu_masses, nu table pointer (host memory here)
+  double om = 0;
+  std::vector<double> nu_tab;            // [n][6] = {r1, dr1, p1, dp1, ddr1, ddp1}
+  std::vector<double> a, h, x, ch, cx;   // nb + 2 nodes, ascending a, + natural-spline coefficients
+  double noghost_previous = 0, cs2_previous = 0;
+  bool ready = false;
+};
+HostGal G;
+
+constexpr int NB = 29999;  // camb/galileon.cc:72 (30 000 nodes)
+
+void nu_pressures(double a, double* rhonu, double* pnu) {
+  for (int i = 0; i < G.M.n_eig; i++) Nu_background(G.M, a * G.M.nu_masses[i], rhonu[i], pnu[i]);
+}
+
+// d(hbar, dpi/da, pi)/da, camb/galileon.cc:254-302
+void rhs(double a, const double y[3], double f[3]) {
+  const DevModel& M = G.M;
+  const double c2 = M.c2, c3 = M.c3, c4 = M.c4, c5 = M.c5, cG = M.cG, h0 = M.h0, orad = M.orad;
+  const double prod = a * y[0] * y[1];
+  const double prod2 = prod * prod, prod3 = prod * prod2, prod4 = prod * prod3, prod5 = prod * prod4;
+  const double h = y[0], h2 = h * h, h3 = h * h2, h4 = h2 * h2, a2 = a * a;
+  const double alpha = c2 / 6.0 * prod - 3 * c3 * h * prod2 + 15 * c4 * h2 * prod3 - 17.5 * c5 * h3 * prod4 - 3.0 * cG * h2 * prod;
+  const double gamma = c2 / 3.0 * h * prod - c3 * h2 * prod2 + 2.5 * c5 * h4 * prod4 - 2.0 * cG * h3 * prod;
+  const double beta = c2 / 6.0 * h2 - 2 * c3 * h3 * prod + 9 * c4 * h4 * prod2 - 10 * c5 * h4 * h * prod3 - cG * h4;
+  const double sigma = 2.0 * h + 2.0 * c3 * prod3 - 15.0 * c4 * h * prod4 + 21.0 * c5 * h2 * prod5 + 6.0 * cG * h * prod2;
+  double lambda = 3.0 * h2 + orad / (a2 * a2) + c2 / 2.0 * prod2 - 2.0 * c3 * h * prod3 + 7.5 * c4 * h2 * prod4 -
+                  9.0 * c5 * h3 * prod5 - cG * h2 * prod2;
+  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
+  nu_pressures(a, rhonu, pnu);
+  for (int i = 0; i < M.n_eig; i++) lambda += M.grhormass[i] * pnu[i] / (a2 * a2 * h0 * h0);
+  const double omega = 2 * c3 * h2 * prod2 - 12 * c4 * h3 * prod3 + 15 * c5 * h4 * prod4 + 4.0 * cG * h3 * prod;
+  const double denom = sigma * beta - alpha * omega;
+  f[0] = (omega * gamma - lambda * beta) / (a * denom);
+  f[1] = (alpha * lambda - sigma * gamma) / (a2 * denom) - 2.0 * y[1] / a;
+  f[2] = y[1];
+}
+
+// ghost / Laplace stability of scalar and tensor perturbations at one node, camb/galileon.cc:130-245
+// returns 0 or the number of the failed condition (1 no-ghost, 2 c_s^2, 3 tensor no-ghost, 4 c_T^2)
+int stability(double a, const double y[3]) {
+  const DevModel& M = G.M;
+  const double c2 = M.c2, c3 = M.c3, c4 = M.c4, c5 = M.c5, cG = M.cG, h0 = M.h0, orad = M.orad;
+  const double xgal = a * y[1];
+  const double prod = xgal * y[0];
+  const double prod2 = prod * prod, prod3 = prod * prod2, prod4 = prod * prod3, prod5 = prod * prod4;
+  const double h = y[0], h2 = h * h, h3 = h * h2, h4 = h2 * h2;
+  const double alpha = c2 / 6.0 * prod - 3 * c3 * h * prod2 + 15 * c4 * h2 * prod3 - 17.5 * c5 * h3 * prod4 - 3.0 * cG * h2 * prod;
+  const double gamma = c2 / 3.0 * h * prod - c3 * h2 * prod2 + 2.5 * c5 * h4 * prod4 - 2.0 * cG * h3 * prod;
+  const double beta = -2 * c3 * h3 * prod + c2 / 6.0 * h2 + 9 * c4 * h4 * prod2 - 10 * c5 * h4 * h * prod3 - cG * h4;
+  const double sigma = 2.0 * h + 2.0 * c3 * prod3 - 15.0 * c4 * h * prod4 + 21.0 * c5 * h2 * prod5 + 6.0 * cG * h * prod2;
+  double lambda = 3.0 * h2 + orad / (a * a * a * a) - 2.0 * c3 * h * prod3 + c2 / 2.0 * prod2 + 7.5 * c4 * h2 * prod4 -
+                  9.0 * c5 * h3 * prod5 - cG * h2 * prod2;
+  const double omega = 2 * c3 * h2 * prod2 - 12 * c4 * h3 * prod3 + 15 * c5 * h4 * prod4 + 4.0 * cG * h3 * prod;
+  const double denom = sigma * beta - alpha * omega;
+  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
+  nu_pressures(a, rhonu, pnu);
+  for (int i = 0; i < M.n_eig; i++) lambda += M.grhormass[i] * pnu[i] / (a * a * a * a * h0 * h0);
+  const double dhdlna = (omega * gamma - lambda * beta) / denom;
+  const double dxdlna = (alpha * lambda - sigma * gamma) / denom - xgal;
+  const double k1 = -6 * c4 * h * prod2 * (dhdlna * xgal + h * dxdlna + prod / 3.0) +
+                    c5 * h2 * prod3 * (12 * h * dxdlna + 15 * dhdlna * xgal + 3 * prod) +
+                    2.0 * cG * (dhdlna * prod + h2 * dxdlna + h * prod);
+  const double k2 = -0.5 * c2 + 6 * c3 * h * prod - 27 * c4 * h2 * prod2 + 30 * c5 * h3 * prod3 + 3.0 * cG * h2;
+  const double k3 = -1.0 - 0.5 * c4 * prod4 - 3 * c5 * h * prod4 * (h * dxdlna + dhdlna * xgal) + cG * prod2;
+  const double k4 = -2.0 + 3.0 * c4 * prod4 - 6 * c5 * h * prod5 - 2.0 * cG * prod2;
+  const double k5 = 2 * c3 * prod2 - 12 * c4 * h * prod3 + 15.0 * c5 * h2 * prod4 + 4.0 * cG * h * prod;
+  const double k6 = 0.5 * c2 - 2.0 * c3 * (h2 * dxdlna + dhdlna * prod + 2 * h * prod) +
+                    c4 * (12 * h3 * prod * dxdlna + 18 * h * prod2 * dhdlna + 13 * h2 * prod2) -
+                    c5 * (18 * h2 * h2 * prod2 * dxdlna + 30 * h2 * prod3 * dhdlna + 12 * h3 * prod3) -
+                    cG * (2.0 * h * dhdlna + 3.0 * h2);
+  const double noghost = k2 + 1.5 * k5 * k5 / k4;
+  const double cs2 = (4 * k1 * k4 * k5 - 2 * k3 * k5 * k5 - 2 * k4 * k4 * k6) / (k4 * (2 * k4 * k2 + 3 * k5 * k5));
+  if (a == 1) {
+    G.noghost_previous = noghost;
+    G.cs2_previous = cs2;
+  }
+  const double noghostt = 0.5 - 0.75 * c4 * prod4 + 1.5 * c5 * prod5 * h + 0.5 * cG * prod2;
+  const double ct2 = (0.5 + 0.25 * c4 * prod4 + 1.5 * c5 * prod4 * h * (h * dxdlna + dhdlna * xgal) - 0.5 * cG * prod2) / noghostt;
+  if (noghost > -1.0 && noghost > -1e-8) return 1;
+  if (cs2 < 0) return 2;
+  if (noghostt < 0) return 3;
+  if (ct2 < 0) return 4;
+  if (noghost > -1.0 && noghost < -1e-8 && std::fabs((noghost - G.noghost_previous) / noghost) > 0.25) return 1;
+  G.noghost_previous = noghost;
+  if (std::fabs((cs2 - G.cs2_previous) / G.cs2_previous) > 1) return 2;
+  G.cs2_previous = cs2;
+  return 0;
+}
+
+// Fehlberg 4(5) embedded pair (published tableau), first-same-as-last derivative handed in and out like GSL's rkf45
+struct Rkf45 {
+  void step(double t, double h, double y[3], double yerr[3], const double k1[3], double dydt_out[3]) const {
+    static const double c[] = {1.0 / 4.0, 3.0 / 8.0, 12.0 / 13.0, 1.0, 1.0 / 2.0};
+    static const double a2[] = {1.0 / 4.0};
+    static const double a3[] = {3.0 / 32.0, 9.0 / 32.0};
+    static const double a4[] = {1932.0 / 2197.0, -7200.0 / 2197.0, 7296.0 / 2197.0};
+    static const double a5[] = {8341.0 / 4104.0, -32832.0 / 4104.0, 29440.0 / 4104.0, -845.0 / 4104.0};
+    static const double a6[] = {-6080.0 / 20520.0, 41040.0 / 20520.0, -28352.0 / 20520.0, 9295.0 / 20520.0, -5643.0 / 20520.0};
+    static const double b[] = {902880.0 / 7618050.0, 0.0, 3953664.0 / 7618050.0, 3855735.0 / 7618050.0, -1371249.0 / 7618050.0,
+                               277020.0 / 7618050.0};
+    static const double e[] = {1.0 / 360.0, 0.0, -128.0 / 4275.0, -2197.0 / 75240.0, 1.0 / 50.0, 2.0 / 55.0};
+    double k[6][3], yt[3];
+    for (int i = 0; i < 3; i++) k[0][i] = k1[i];
+    const double* const rows[] = {a2, a3, a4, a5, a6};
+    for (int s = 1; s < 6; s++) {
+      for (int i = 0; i < 3; i++) {
+        double acc = rows[s - 1][0] * k[0][i];
+        for (int j = 1; j < s; j++) acc += rows[s - 1][j] * k[j][i];
+        yt[i] = y[i] + (s == 1 ? rows[0][0] * h * k[0][i] : h * acc);
+      }
+      rhs(t + c[s - 1] * h, yt, k[s]);
+    }
+    for (int i = 0; i < 3; i++) {
+      const double d = b[0] * k[0][i] + b[2] * k[2][i] + b[3] * k[3][i] + b[4] * k[4][i] + b[5] * k[5][i];
+      y[i] += h * d;
+    }
+    rhs(t + h, y, dydt_out);
+    for (int i = 0; i < 3; i++)
+      yerr[i] = h * (e[0] * k[0][i] + e[2] * k[2][i] + e[3] * k[3][i] + e[4] * k[4][i] + e[5] * k[5][i]);
+  }
+};
+
+// one accepted step towards t1 with the standard y-error controller (eps_abs 1e-18, eps_rel 1e-16, a_y = 1, a_dydt = 0)
+void evolve_apply(double& t, double t1, double& h, double y[3]) {
+  const double eps_abs = 1e-18, eps_rel = 1e-16, S = 0.9, ord = 5.0;
+  const Rkf45 stepper;
+  const double t0 = t, dt = t1 - t0;
+  double h0 = h;
+  const double y0[3] = {y[0], y[1], y[2]};
+  double yerr[3], dydt_in[3], dydt_out[3];
+  rhs(t0, y, dydt_in);
+  for (;;) {
+    const bool final_step = (dt >= 0.0 && h0 > dt) || (dt < 0.0 && h0 < dt);
+    if (final_step) h0 = dt;
+    stepper.step(t0, h0, y, yerr, dydt_in, dydt_out);
+    t = final_step ? t1 : t0 + h0;
+    const double h_old = h0;
+    double rmax = 2.2250738585072014e-308;
+    for (int i = 0; i < 3; i++) rmax = std::fmax(rmax, std::fabs(yerr[i]) / std::fabs(eps_rel * std::fabs(y[i]) + eps_abs));
+    if (rmax > 1.1) {  // shrink and retry from (t0, y0) unless the step cannot shrink any more
+      h0 = h_old * std::fmax(0.2, S / std::pow(rmax, 1.0 / ord));
+      if (std::fabs(h0) < std::fabs(h_old) && t + h0 != t) {
+        for (int i = 0; i < 3; i++) y[i] = y0[i];
+        continue;
+      }
+      h0 = h_old;
+    } else if (rmax < 0.5) {
+      h0 = h_old * std::fmin(5.0, std::fmax(1.0, S / std::pow(rmax, 1.0 / (ord + 1.0))));
+    }
+    break;
+  }
+  h = h0;
+}
+
+// natural cubic spline, c[i] = y''(x_i)/2 (gsl_interp_cspline's representation)
+void spline_coefficients(const std::vector<double>& xa, const std::vector<double>& ya, std::vector<double>& c) {
+  const int n = (int)xa.size(), sys = n - 2;
+  c.assign(n, 0.0);
+  std::vector<double> rhs_(sys), diag(sys), off(sys), al(sys), ga(sys), z(sys);
+  for (int i = 0; i < sys; i++) {
+    const double h_i = xa[i + 1] - xa[i], h_ip1 = xa[i + 2] - xa[i + 1];
+    const double yd_i = ya[i + 1] - ya[i], yd_ip1 = ya[i + 2] - ya[i + 1];
+    const double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0, g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
+    off[i] = h_ip1;
+    diag[i] = 2.0 * (h_ip1 + h_i);
+    rhs_[i] = 3.0 * (yd_ip1 * g_ip1 - yd_i * g_i);
+  }
+  al[0] = diag[0];
+  ga[0] = off[0] / al[0];
+  for (int i = 1; i < sys - 1; i++) {
+    al[i] = diag[i] - off[i - 1] * ga[i - 1];
+    ga[i] = off[i] / al[i];
+  }
+  if (sys > 1) al[sys - 1] = diag[sys - 1] - off[sys - 2] * ga[sys - 2];
+  z[0] = rhs_[0];
+  for (int i = 1; i < sys; i++) z[i] = rhs_[i] - ga[i - 1] * z[i - 1];
+  for (int i = 0; i < sys; i++) z[i] = z[i] / al[i];
+  c[sys] = z[sys - 1];
+  for (int i = sys - 2; i >= 0; i--) c[i + 1] = z[i] - ga[i] * c[i + 2];
+}
+
+double spline_eval(const std::vector<double>& xa, const std::vector<double>& ya, const std::vector<double>& c, double x) {
+  int lo = 0, hi = (int)xa.size() - 1;
+  while (hi > lo + 1) {
+    const int mid = (hi + lo) / 2;
+    if (xa[mid] > x)
+      hi = mid;
+    else
+      lo = mid;
+  }
+  const double dx = xa[lo + 1] - xa[lo], dy = ya[lo + 1] - ya[lo], delx = x - xa[lo];
+  const double b_i = (dy / dx) - dx * (c[lo + 1] + 2.0 * c[lo]) / 3.0;
+  const double d_i = (c[lo + 1] - c[lo]) / (3.0 * dx);
+  return ya[lo] + delx * (b_i + delx * (c[lo] + delx * d_i));
+}
+
+}  // namespace
+
+extern "C" {
+
+int galileon_set_nu_tables_(const double* r1, const double* p1, const double* dr1, const double* dp1, const double* ddr1,
+                            const double* ddp1, const int* n, const double* dlnam) {
+  if (*n < 2) return 5;
+  G.nu_tab.resize((size_t)*n * 6);
+  for (int i = 0; i < *n; i++) {
+    double* row = &G.nu_tab[(size_t)i * 6];
+    row[0] = r1[i]; row[1] = dr1[i]; row[2] = p1[i]; row[3] = dp1[i]; row[4] = ddr1[i]; row[5] = ddp1[i];
+  }
+  G.M.nu_tab = G.nu_tab.data();
+  G.M.dlnam = *dlnam;
+  G.M.inv_dlnam = 1.0 / *dlnam;
+  return 0;
+}
+
+// camb/galileon.cc:503-688 with calcHubbleGalileon (:332-438)
+int arrays_(double* omegar, double* omegam, double* H0in, double* c2in, double* c3in, double* c4in, double* cGin,
+            double* grhormass, double* nu_masses, int* nu_mass_eigenstates) {
+  G.ready = false;
+  DevModel& M = G.M;
+  const int neig = *nu_mass_eigenstates;
+  if (neig < 0 || neig > GC_MAX_NU) return 5;
+  if (neig > 0 && G.nu_tab.empty()) return 5;  // galileon_set_nu_tables_ first
+  M.n_eig = neig;
+  for (int i = 0; i < neig; i++) {
+    M.grhormass[i] = grhormass[i];
+    M.nu_masses[i] = nu_masses[i];
+  }
+  G.om = *omegam;
+  M.orad = *omegar;
+  M.h0 = *H0in;
+  M.c2 = *c2in;
+  M.cG = *cGin;
+  const double grhom = 3 * (M.h0 * M.h0);
+  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
+  nu_pressures(1.0, rhonu, pnu);
+  double nu_closure = 0;  // sum_i rho_nu,i(a=1) grhormass_i / grhom
+  // flatness closure: the highest non-zero coefficient follows from the others (:520-575)
+  if (*c3in == 0 && *c4in == 0) {
+    M.c3 = 0.5 * (-1. + G.om + M.orad + M.c2 / 6. - 3 * M.cG);
+    for (int i = 0; i < neig; i++) M.c3 += 0.5 * rhonu[i] * M.grhormass[i] / grhom;
+    M.c4 = 0;
+    M.c5 = 0;
+  } else if (*c4in == 0) {
+    M.c3 = *c3in;
+    // the reference's right-hand side reads the c4 left over from the previous call (:546); kept
+    M.c4 = (1. - G.om - M.orad - M.c2 / 6. + 2 * M.c3 - 7.5 * M.c4 + 3 * M.cG) / 7.5;
+    for (int i = 0; i < neig; i++) M.c4 += -rhonu[i] * M.grhormass[i] / (7.5 * grhom);
+    M.c5 = 0;
+  } else {
+    M.c3 = *c3in;
+    M.c4 = *c4in;
+    M.c5 = (-1. + G.om + M.orad + M.c2 / 6. - 2 * M.c3 + 7.5 * M.c4 - 3 * M.cG) / 7.;
+    for (int i = 0; i < neig; i++) M.c5 += rhonu[i] * M.grhormass[i] / (7. * grhom);
+  }
+  (void)nu_closure;
+  const double amin = 1e-10, amax = 1.;
+  const double q = std::pow(amin / amax, 1. / NB);
+  std::vector<double> grid(NB + 1), hub(NB + 1), xg(NB + 1);
+  for (int i = 0; i <= NB; i++) grid[i] = amax * std::pow(q, i);
+  // integrate from a = 1 (hbar = 1, dpi/da = 1) down to amin, checking every node
+  double y[3] = {1.0, 1.0, 0.0};
+  double a = 1, h = -1e-6;
+  for (int i = 0; i <= NB; ++i) {
+    while (a > grid[i]) evolve_apply(a, grid[i], h, y);
+    if (std::isnan(y[0]) || std::isnan(y[1]) || std::isnan(y[2])) return 8;
+    if (stability(a, y)) return 7;
+    const double h2 = y[0] * y[0];
+    const double x1 = a * y[1], x2 = x1 * x1, x3 = x2 * x1, a3 = a * a * a;
+    const double OmegaP = (0.5 * M.c2 * x2 - 6.0 * M.c3 * h2 * x3 + 22.5 * M.c4 * h2 * h2 * x2 * x2 -
+                           21.0 * M.c5 * h2 * h2 * h2 * x3 * x2 - 9.0 * M.cG * h2 * x2) / 3.0;
+    double OmegaM = 1 - OmegaP - M.orad / (a3 * a * h2);
+    nu_pressures(grid[i], rhonu, pnu);
+    for (int j = 0; j < neig; j++) OmegaM -= M.grhormass[j] * rhonu[j] / (a3 * a * 3. * h2 * (M.h0 * M.h0));
+    const double OmTest = G.om / (a3 * h2);
+    if (std::fabs((OmegaM - OmTest) / OmTest) > 1e-4) return 4;  // Friedmann closure (:420)
+    hub[i] = y[0];
+    xg[i] = y[1];
+  }
+  const int n = NB + 2;
+  G.a.assign(n, 0);
+  G.h.assign(n, 0);
+  G.x.assign(n, 0);
+  for (int i = 0; i <= NB; i++) {
+    G.a[i] = grid[NB - i];
+    G.h[i] = hub[NB - i];
+    G.x[i] = xg[NB - i];
+  }
+  // one linearly extrapolated node beyond a = 1 (:655-663)
+  G.a[NB + 1] = 1. / q;
+  G.h[NB + 1] = (G.h[NB] - G.h[NB - 1]) / (G.a[NB] - G.a[NB - 1]) * (G.a[NB + 1] - G.a[NB - 1]) + G.h[NB - 1];
+  G.x[NB + 1] = (G.x[NB] - G.x[NB - 1]) / (G.a[NB] - G.a[NB - 1]) * (G.a[NB + 1] - G.a[NB - 1]) + G.x[NB - 1];
+  spline_coefficients(G.a, G.h, G.ch);
+  spline_coefficients(G.a, G.x, G.cx);
+  G.ready = true;
+  return 0;
+}
+
+void freegal_(void) {
+  G.a.clear(); G.h.clear(); G.x.clear(); G.ch.clear(); G.cx.clear();
+  G.ready = false;
+}
+
+// the tabulated background for galcamb_model.gal_a / gal_h / gal_x (the accessor INTEGRATION.md asks galileon.cc for)
+int galgettable_(const double** a, const double** h, const double** x, int* n) {
+  if (!G.ready) return 6;
+  *a = G.a.data();
+  *h = G.h.data();
+  *x = G.x.data();
+  *n = NB + 1;  // without the extrapolated node (the device library appends its own)
+  return 0;
+}
+
+int galgetcoefficients_(double* c2, double* c3, double* c4, double* c5, double* cG) {
+  *c2 = G.M.c2; *c3 = G.M.c3; *c4 = G.M.c4; *c5 = G.M.c5; *cG = G.M.cG;
+  return G.ready ? 0 : 6;
+}
+
+double GetX_(double* point) {
+  if (!G.ready || !(*point >= 0.0 && *point <= 1.1)) return std::nan("");
+  return *point * spline_eval(G.a, G.x, G.cx, *point);
+}
+
+double GetH_(double* point) {
+  if (!G.ready || !(*point >= 0.0 && *point <= 1.1)) return std::nan("");
+  return spline_eval(G.a, G.h, G.ch, *point);
+}
+
+void GetdHdX_(double* point, double* hcamb, double* xcamb, double& dh, double& dx, double* grhormass, double* nu_masses,
+              int* nu_mass_eigenstates) {
+  (void)grhormass; (void)nu_masses; (void)nu_mass_eigenstates;  // the values given to arrays_ are in use
+  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
+  nu_pressures(*point, rhonu, pnu);
+  gc::gal_GetdHdX(G.M, *point, *hcamb, *xcamb, pnu, dh, dx);
+}
+
+double ct_(double* point, double* grhormass, double* nu_masses, int* nu_mass_eigenstates) {
+  double xgal = GetX_(point), h = GetH_(point), ha = *point * h, dh = 0, dx = 0;
+  const double prod = xgal * h, prod2 = prod * prod, prod4 = prod2 * prod2, prod5 = prod4 * prod;
+  GetdHdX_(point, &ha, &xgal, dh, dx, grhormass, nu_masses, nu_mass_eigenstates);
+  const double c4 = G.M.c4, c5 = G.M.c5, cG = G.M.cG;
+  return std::sqrt((0.5 + 0.25 * c4 * prod4 + 1.5 * c5 * prod4 * h * (h * dx + dh * xgal) - 0.5 * cG * prod2) /
+                   (0.5 - 0.75 * c4 * prod4 + 1.5 * c5 * prod5 * h + 0.5 * cG * prod2));
+}
+
+double grhogal_(double* point, double* hcamb, double* xcamb) { return gc::gal_grhogal(G.M, *point, *hcamb, *xcamb); }
+
+double gpresgal_(double* point, double* hcamb, double* xcamb, double* dhcamb, double* dxcamb) {
+  return gc::gal_gpresgal(G.M, *point, *hcamb, *xcamb, *dhcamb, *dxcamb);
+}
+
+double Chigal_(double* point, double* hcamb, double* xcamb, double* dgrho, double* eta, double* dphi, double* dphiprime,
+               double* k) {
+  return gc::gal_Chigal(G.M, *point, *hcamb, *xcamb, *dgrho, *eta, *dphi, *dphiprime, *k);
+}
+
+double qgal_(double* point, double* hcamb, double* xcamb, double* dgq, double* eta, double* dphi, double* dphiprime, double* k) {
+  return gc::gal_qgal(G.M, *point, *hcamb, *xcamb, *dgq, *eta, *dphi, *dphiprime, *k);
+}
+
+double Pigal_(double* point, double* hcamb, double* xcamb, double* dhcamb, double* dxcamb, double* dgrho, double* dgq,
+              double* dgpi, double* eta, double* dphi, double* k) {
+  return gc::gal_Pigal(G.M, *point, *hcamb, *xcamb, *dhcamb, *dxcamb, *dgrho, *dgq, *dgpi, *eta, *dphi, *k);
+}
+
+double dphisecond_(double* point, double* hcamb, double* xcamb, double* dhcamb, double* dxcamb, double* dgrho, double* dgq,
+                   double* eta, double* dphi, double* dphiprime, double* k, double* deltafprime) {
+  return gc::gal_dphisecond(G.M, *point, *hcamb, *xcamb, *dhcamb, *dxcamb, *dgrho, *dgq, *eta, *dphi, *dphiprime, *k,
+                            *deltafprime);
+}
+
+double pigalprime_(double* point, double* hcamb, double* xcamb, double* dhcamb, double* dxcamb, double* dgrho, double* dgq,
+                   double* dgpi, double* pidot, double* eta, double* dphi, double* dphiprime, double* k, double* grho,
+                   double* gpres, double* grhormass, double* nu_masses, int* nu_mass_eigenstates) {
+  (void)grhormass; (void)nu_masses; (void)nu_mass_eigenstates;
+  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
+  nu_pressures(*point, rhonu, pnu);
+  return gc::gal_pigalprime(G.M, *point, *hcamb, *xcamb, *dhcamb, *dxcamb, *dgrho, *dgq, *dgpi, *pidot, *eta, *dphi,
+                            *dphiprime, *k, *grho, *gpres, pnu);
+}
+
+}  // extern "C"

@@ -12,13 +12,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     h = open(os.path.join(ROOT, "include", "galcamb.h")).read()
-    return sorted(set(re.findall(r"\b(galcamb_[a-z_]+_)\s*\(", h)))
+    syms = set(re.findall(r"\b(galcamb_[a-z_0-9]+_)\s*\(", h))
+    # the reference's own symbols (camb/interface.f90) and the two table accessors, include/galileon_abi.h
+    g = open(os.path.join(ROOT, "include", "galileon_abi.h")).read()
+    syms |= set(re.findall(r"^(?:int|double|void)\s+([A-Za-z_]+_)\s*\(", g, flags=re.M))
+    return sorted(syms)
 
 
 def test_library_exports_every_declared_symbol(built_cuda_lib):
     L = C.CDLL(built_cuda_lib)
     syms = declared_symbols()
-    assert len(syms) >= 18
+    assert len(syms) >= 18 + 15
+    assert {"arrays_", "GetX_", "GetH_", "GetdHdX_", "ct_", "pigalprime_", "freegal_"} <= set(syms)
     for s in syms:
         assert hasattr(L, s), s
 
