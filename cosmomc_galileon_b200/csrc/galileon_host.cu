@@ -20,25 +20,33 @@ namespace {
 
 using gc::Nu_background;
 
-struct HostGal {
+// one background problem: the constants of the ODE + the memory of the two "no sudden jump" stability tests
+struct Background {
   DevModel M{};  // constants c2..c5, cG, h0, orad, n_eig, grhormass, nu_masses, nu table pointer (host memory here)
+  double noghost_previous = 0, cs2_previous = 0;
+  void nu_pressures(double a, double* rhonu, double* pnu) const {
+    for (int i = 0; i < M.n_eig; i++) gc::Nu_background(M, a * M.nu_masses[i], rhonu[i], pnu[i]);
+  }
+  void rhs(double a, const double y[3], double f[3]) const;
+  int stability(double a, const double y[3]);
+  void evolve_apply(double& t, double t1, double& h, double y[3]) const;
+  int run(double om, bool reject_negative_density, std::vector<double>& grid, std::vector<double>& hub, std::vector<double>& xg);
+};
+
+struct HostGal : Background {
   double om = 0;
   std::vector<double> nu_tab;            // [n][6] = {r1, dr1, p1, dp1, ddr1, ddp1}
   std::vector<double> a, h, x, ch, cx;   // nb + 2 nodes, ascending a, + natural-spline coefficients
-  double noghost_previous = 0, cs2_previous = 0;
   bool ready = false;
 };
 HostGal G;
 
 constexpr int NB = 29999;  // camb/galileon.cc:72 (30 000 nodes)
 
-void nu_pressures(double a, double* rhonu, double* pnu) {
-  for (int i = 0; i < G.M.n_eig; i++) Nu_background(G.M, a * G.M.nu_masses[i], rhonu[i], pnu[i]);
-}
+void nu_pressures(double a, double* rhonu, double* pnu) { G.nu_pressures(a, rhonu, pnu); }
 
 // d(hbar, dpi/da, pi)/da, camb/galileon.cc:254-302
-void rhs(double a, const double y[3], double f[3]) {
-  const DevModel& M = G.M;
+void Background::rhs(double a, const double y[3], double f[3]) const {
   const double c2 = M.c2, c3 = M.c3, c4 = M.c4, c5 = M.c5, cG = M.cG, h0 = M.h0, orad = M.orad;
   const double prod = a * y[0] * y[1];
   const double prod2 = prod * prod, prod3 = prod * prod2, prod4 = prod * prod3, prod5 = prod * prod4;
@@ -61,8 +69,7 @@ void rhs(double a, const double y[3], double f[3]) {
 
 // ghost / Laplace stability of scalar and tensor perturbations at one node, camb/galileon.cc:130-245
 // returns 0 or the number of the failed condition (1 no-ghost, 2 c_s^2, 3 tensor no-ghost, 4 c_T^2)
-int stability(double a, const double y[3]) {
-  const DevModel& M = G.M;
+int Background::stability(double a, const double y[3]) {
   const double c2 = M.c2, c3 = M.c3, c4 = M.c4, c5 = M.c5, cG = M.cG, h0 = M.h0, orad = M.orad;
   const double xgal = a * y[1];
   const double prod = xgal * y[0];
@@ -95,8 +102,8 @@ int stability(double a, const double y[3]) {
   const double noghost = k2 + 1.5 * k5 * k5 / k4;
   const double cs2 = (4 * k1 * k4 * k5 - 2 * k3 * k5 * k5 - 2 * k4 * k4 * k6) / (k4 * (2 * k4 * k2 + 3 * k5 * k5));
   if (a == 1) {
-    G.noghost_previous = noghost;
-    G.cs2_previous = cs2;
+    noghost_previous = noghost;
+    cs2_previous = cs2;
   }
   const double noghostt = 0.5 - 0.75 * c4 * prod4 + 1.5 * c5 * prod5 * h + 0.5 * cG * prod2;
   const double ct2 = (0.5 + 0.25 * c4 * prod4 + 1.5 * c5 * prod4 * h * (h * dxdlna + dhdlna * xgal) - 0.5 * cG * prod2) / noghostt;
@@ -104,15 +111,16 @@ int stability(double a, const double y[3]) {
   if (cs2 < 0) return 2;
   if (noghostt < 0) return 3;
   if (ct2 < 0) return 4;
-  if (noghost > -1.0 && noghost < -1e-8 && std::fabs((noghost - G.noghost_previous) / noghost) > 0.25) return 1;
-  G.noghost_previous = noghost;
-  if (std::fabs((cs2 - G.cs2_previous) / G.cs2_previous) > 1) return 2;
-  G.cs2_previous = cs2;
+  if (noghost > -1.0 && noghost < -1e-8 && std::fabs((noghost - noghost_previous) / noghost) > 0.25) return 1;
+  noghost_previous = noghost;
+  if (std::fabs((cs2 - cs2_previous) / cs2_previous) > 1) return 2;
+  cs2_previous = cs2;
   return 0;
 }
 
 // Fehlberg 4(5) embedded pair (published tableau), first-same-as-last derivative handed in and out like GSL's rkf45
 struct Rkf45 {
+  const Background& B;
   void step(double t, double h, double y[3], double yerr[3], const double k1[3], double dydt_out[3]) const {
     static const double c[] = {1.0 / 4.0, 3.0 / 8.0, 12.0 / 13.0, 1.0, 1.0 / 2.0};
     static const double a2[] = {1.0 / 4.0};
@@ -132,22 +140,22 @@ struct Rkf45 {
         for (int j = 1; j < s; j++) acc += rows[s - 1][j] * k[j][i];
         yt[i] = y[i] + (s == 1 ? rows[0][0] * h * k[0][i] : h * acc);
       }
-      rhs(t + c[s - 1] * h, yt, k[s]);
+      B.rhs(t + c[s - 1] * h, yt, k[s]);
     }
     for (int i = 0; i < 3; i++) {
       const double d = b[0] * k[0][i] + b[2] * k[2][i] + b[3] * k[3][i] + b[4] * k[4][i] + b[5] * k[5][i];
       y[i] += h * d;
     }
-    rhs(t + h, y, dydt_out);
+    B.rhs(t + h, y, dydt_out);
     for (int i = 0; i < 3; i++)
       yerr[i] = h * (e[0] * k[0][i] + e[2] * k[2][i] + e[3] * k[3][i] + e[4] * k[4][i] + e[5] * k[5][i]);
   }
 };
 
 // one accepted step towards t1 with the standard y-error controller (eps_abs 1e-18, eps_rel 1e-16, a_y = 1, a_dydt = 0)
-void evolve_apply(double& t, double t1, double& h, double y[3]) {
+void Background::evolve_apply(double& t, double t1, double& h, double y[3]) const {
   const double eps_abs = 1e-18, eps_rel = 1e-16, S = 0.9, ord = 5.0;
-  const Rkf45 stepper;
+  const Rkf45 stepper{*this};
   const double t0 = t, dt = t1 - t0;
   double h0 = h;
   const double y0[3] = {y[0], y[1], y[2]};
@@ -218,6 +226,72 @@ double spline_eval(const std::vector<double>& xa, const std::vector<double>& ya,
   return ya[lo] + delx * (b_i + delx * (c[lo] + delx * d_i));
 }
 
+// calcHubbleGalileon, camb/galileon.cc:332-438 (= calcHubble, camb/theta.cc:179-295, which also rejects a negative
+// Galileon density): from a = 1 (hbar = 1, dpi/da = 1) down to 1e-10 on NB + 1 log-spaced nodes, every node checked
+int Background::run(double om, bool reject_negative_density, std::vector<double>& grid, std::vector<double>& hub,
+                    std::vector<double>& xg) {
+  const double amin = 1e-10, amax = 1.;
+  const double q = std::pow(amin / amax, 1. / NB);
+  grid.resize(NB + 1);
+  hub.assign(NB + 1, 0.0);
+  xg.assign(NB + 1, 0.0);
+  for (int i = 0; i <= NB; i++) grid[i] = amax * std::pow(q, i);
+  double y[3] = {1.0, 1.0, 0.0};
+  double a = 1, h = -1e-6;
+  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
+  for (int i = 0; i <= NB; ++i) {
+    while (a > grid[i]) evolve_apply(a, grid[i], h, y);
+    if (std::isnan(y[0]) || std::isnan(y[1]) || std::isnan(y[2])) return 8;
+    if (stability(a, y)) return 7;
+    const double h2 = y[0] * y[0];
+    const double x1 = a * y[1], x2 = x1 * x1, x3 = x2 * x1, a3 = a * a * a;
+    const double OmegaP = (0.5 * M.c2 * x2 - 6.0 * M.c3 * h2 * x3 + 22.5 * M.c4 * h2 * h2 * x2 * x2 -
+                           21.0 * M.c5 * h2 * h2 * h2 * x3 * x2 - 9.0 * M.cG * h2 * x2) / 3.0;
+    double OmegaM = 1 - OmegaP - M.orad / (a3 * a * h2);
+    nu_pressures(grid[i], rhonu, pnu);
+    for (int j = 0; j < M.n_eig; j++) OmegaM -= M.grhormass[j] * rhonu[j] / (a3 * a * 3. * h2 * (M.h0 * M.h0));
+    const double OmTest = om / (a3 * h2);
+    if (reject_negative_density && OmegaP < 0) return 5;                  // camb/theta.cc:263
+    if (std::fabs((OmegaM - OmTest) / OmTest) > 1e-4) return 4;           // Friedmann closure, camb/galileon.cc:420
+    hub[i] = y[0];
+    xg[i] = y[1];
+  }
+  return 0;
+}
+
+// exact integral of the natural spline between two abscissae (what gsl_spline_eval_integ returns)
+double spline_integral(const std::vector<double>& xa, const std::vector<double>& ya, const std::vector<double>& c,
+                       double a, double b) {
+  auto find = [&](double x) {
+    int lo = 0, hi = (int)xa.size() - 1;
+    while (hi > lo + 1) {
+      const int mid = (hi + lo) / 2;
+      if (xa[mid] > x)
+        hi = mid;
+      else
+        lo = mid;
+    }
+    return lo;
+  };
+  const int ia = find(a), ib = find(b);
+  double result = 0.0;
+  for (int i = ia; i <= ib; i++) {
+    const double x_lo = xa[i], x_hi = xa[i + 1], y_lo = ya[i], dx = x_hi - x_lo, dy = ya[i + 1] - y_lo;
+    const double b_i = (dy / dx) - dx * (c[i + 1] + 2.0 * c[i]) / 3.0;
+    const double c_i = c[i];
+    const double d_i = (c[i + 1] - c[i]) / (3.0 * dx);
+    if (i == ia || i == ib) {
+      const double x1 = (i == ia) ? a : x_lo, x2 = (i == ib) ? b : x_hi;
+      const double r1 = x1 - x_lo, r2 = x2 - x_lo, r12 = r1 + r2, bterm = 0.5 * b_i * r12;
+      const double cterm = (1.0 / 3.0) * c_i * (r1 * r1 + r2 * r2 + r1 * r2), dterm = 0.25 * d_i * r12 * (r1 * r1 + r2 * r2);
+      result += (r2 - r1) * (y_lo + bterm + cterm + dterm);
+    } else {
+      result += dx * (y_lo + dx * (0.5 * b_i + dx * (c_i / 3.0 + 0.25 * d_i * dx)));
+    }
+  }
+  return result;
+}
+
 }  // namespace
 
 extern "C" {
@@ -257,7 +331,6 @@ int arrays_(double* omegar, double* omegam, double* H0in, double* c2in, double* 
   const double grhom = 3 * (M.h0 * M.h0);
   double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
   nu_pressures(1.0, rhonu, pnu);
-  double nu_closure = 0;  // sum_i rho_nu,i(a=1) grhormass_i / grhom
   // flatness closure: the highest non-zero coefficient follows from the others (:520-575)
   if (*c3in == 0 && *c4in == 0) {
     M.c3 = 0.5 * (-1. + G.om + M.orad + M.c2 / 6. - 3 * M.cG);
@@ -276,30 +349,8 @@ int arrays_(double* omegar, double* omegam, double* H0in, double* c2in, double* 
     M.c5 = (-1. + G.om + M.orad + M.c2 / 6. - 2 * M.c3 + 7.5 * M.c4 - 3 * M.cG) / 7.;
     for (int i = 0; i < neig; i++) M.c5 += rhonu[i] * M.grhormass[i] / (7. * grhom);
   }
-  (void)nu_closure;
-  const double amin = 1e-10, amax = 1.;
-  const double q = std::pow(amin / amax, 1. / NB);
-  std::vector<double> grid(NB + 1), hub(NB + 1), xg(NB + 1);
-  for (int i = 0; i <= NB; i++) grid[i] = amax * std::pow(q, i);
-  // integrate from a = 1 (hbar = 1, dpi/da = 1) down to amin, checking every node
-  double y[3] = {1.0, 1.0, 0.0};
-  double a = 1, h = -1e-6;
-  for (int i = 0; i <= NB; ++i) {
-    while (a > grid[i]) evolve_apply(a, grid[i], h, y);
-    if (std::isnan(y[0]) || std::isnan(y[1]) || std::isnan(y[2])) return 8;
-    if (stability(a, y)) return 7;
-    const double h2 = y[0] * y[0];
-    const double x1 = a * y[1], x2 = x1 * x1, x3 = x2 * x1, a3 = a * a * a;
-    const double OmegaP = (0.5 * M.c2 * x2 - 6.0 * M.c3 * h2 * x3 + 22.5 * M.c4 * h2 * h2 * x2 * x2 -
-                           21.0 * M.c5 * h2 * h2 * h2 * x3 * x2 - 9.0 * M.cG * h2 * x2) / 3.0;
-    double OmegaM = 1 - OmegaP - M.orad / (a3 * a * h2);
-    nu_pressures(grid[i], rhonu, pnu);
-    for (int j = 0; j < neig; j++) OmegaM -= M.grhormass[j] * rhonu[j] / (a3 * a * 3. * h2 * (M.h0 * M.h0));
-    const double OmTest = G.om / (a3 * h2);
-    if (std::fabs((OmegaM - OmTest) / OmTest) > 1e-4) return 4;  // Friedmann closure (:420)
-    hub[i] = y[0];
-    xg[i] = y[1];
-  }
+  std::vector<double> grid, hub, xg;
+  if (int status = G.run(G.om, false, grid, hub, xg)) return status;
   const int n = NB + 2;
   G.a.assign(n, 0);
   G.h.assign(n, 0);
@@ -310,6 +361,7 @@ int arrays_(double* omegar, double* omegam, double* H0in, double* c2in, double* 
     G.x[i] = xg[NB - i];
   }
   // one linearly extrapolated node beyond a = 1 (:655-663)
+  const double q = std::pow(1e-10 / 1., 1. / NB);
   G.a[NB + 1] = 1. / q;
   G.h[NB + 1] = (G.h[NB] - G.h[NB - 1]) / (G.a[NB] - G.a[NB - 1]) * (G.a[NB + 1] - G.a[NB - 1]) + G.h[NB - 1];
   G.x[NB + 1] = (G.x[NB] - G.x[NB - 1]) / (G.a[NB] - G.a[NB - 1]) * (G.a[NB + 1] - G.a[NB - 1]) + G.x[NB - 1];
@@ -317,6 +369,62 @@ int arrays_(double* omegar, double* omegam, double* H0in, double* c2in, double* 
   spline_coefficients(G.a, G.x, G.cx);
   G.ready = true;
   return 0;
+}
+
+// camb/theta.cc:296-426 -- theta = r_s(a*) / D_A(a*) for the theta <-> H0 solve of CosmoMC
+// (source/CosmologyParameterizations.f90:263-271).  Its own background problem: the tables of arrays_ are untouched.
+// h0 in km/s/Mpc here.  Returns -1 when the background is rejected, like the reference (:380).
+double theta_(double* omegam, double* orad, double* ombh2, double* h0, double* astar, double* c2in, double* c3in, double* c4in,
+              double* cGin, double* grhormass, double* nu_masses, int* nu_mass_eigenstates) {
+  const int neig = *nu_mass_eigenstates;
+  if (neig < 0 || neig > GC_MAX_NU || (neig > 0 && G.nu_tab.empty())) return -1;
+  const double cl = 2.99792458e8;
+  Background B;
+  DevModel& M = B.M;
+  M.nu_tab = G.M.nu_tab;
+  M.dlnam = G.M.dlnam;
+  M.inv_dlnam = G.M.inv_dlnam;
+  M.n_eig = neig;
+  for (int i = 0; i < neig; i++) {
+    M.grhormass[i] = grhormass[i];
+    M.nu_masses[i] = nu_masses[i];
+  }
+  const double om = *omegam;
+  M.orad = *orad;
+  M.h0 = *h0 * 1000 / cl;
+  M.c2 = *c2in;
+  M.cG = *cGin;
+  const double grhom = 3 * (M.h0 * M.h0);
+  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
+  B.nu_pressures(1.0, rhonu, pnu);
+  if (*c3in == 0 && *c4in == 0) {
+    M.c3 = 0.5 * (-1. + om + M.orad + M.c2 / 6. - 3 * M.cG);
+    for (int i = 0; i < neig; i++) M.c3 += 0.5 * rhonu[i] * M.grhormass[i] / grhom;
+    M.c4 = M.c5 = 0;
+  } else if (*c4in == 0) {
+    M.c3 = *c3in;
+    M.c4 = (1. - om - M.orad - M.c2 / 6. + 2 * M.c3 + 3 * M.cG) / 7.5;  // local c4 = 0 on the right-hand side (:329)
+    for (int i = 0; i < neig; i++) M.c4 += -rhonu[i] * M.grhormass[i] / (7.5 * grhom);
+    M.c5 = 0;
+  } else {
+    M.c3 = *c3in;
+    M.c4 = *c4in;
+    M.c5 = (-1. + om + M.orad + M.c2 / 6. - 2 * M.c3 + 7.5 * M.c4 - 3 * M.cG) / 7.;
+    for (int i = 0; i < neig; i++) M.c5 += rhonu[i] * M.grhormass[i] / (7. * grhom);
+  }
+  std::vector<double> grid, hub, xg;
+  if (B.run(om, true, grid, hub, xg)) return -1;
+  const int n = NB + 1;
+  std::vector<double> av(n), rs(n), da(n), crs, cda;
+  for (int i = 0; i < n; i++) {
+    const double a = grid[NB - i], hb = hub[NB - i];
+    av[i] = a;
+    rs[i] = cl / (a * a * hb * (*h0) * 1000 * std::sqrt(3 * (1 + 3e4 * a * (*ombh2))));
+    da[i] = cl / (a * a * hb * (*h0) * 1000);
+  }
+  spline_coefficients(av, rs, crs);
+  spline_coefficients(av, da, cda);
+  return spline_integral(av, rs, crs, 1e-8, *astar) / spline_integral(av, da, cda, *astar, 1.0);
 }
 
 void freegal_(void) {

@@ -49,6 +49,11 @@ double pigalprime_(double* point, double* hcamb, double* xcamb, double* dhcamb, 
                    double* dgpi, double* pidot, double* eta, double* dphi, double* dphiprime, double* k, double* grho,
                    double* gpres, double* grhormass, double* nu_masses, int* nu_mass_eigenstates); /* :1084 */
 
+/* camb/theta.cc:296 -- theta = r_s(a*)/D_A(a*) for CosmoMC's theta <-> H0 solve (source/CosmologyParameterizations.f90:
+ * 263-271).  h0 in km/s/Mpc.  Runs its own background integration (arrays_' tables are untouched); -1 = rejected. */
+double theta_(double* omegam, double* orad, double* ombh2, double* h0, double* astar, double* c2in, double* c3in, double* c4in,
+              double* cGin, double* grhormass, double* nu_masses, int* nu_mass_eigenstates);
+
 /* Not in the reference: the tabulated background (ascending a, 30 000 nodes) and the closed coefficients, i.e. what
  * galcamb_model.gal_a/gal_h/gal_x and c2..c5,cG are filled from. */
 int galgettable_(const double** a, const double** h, const double** x, int* n);

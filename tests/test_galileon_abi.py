@@ -115,3 +115,29 @@ def test_unstable_point_is_rejected_with_a_status(lib, oracle):
     assert rc == 0
     lib.freegal_()
     assert np.isnan(lib.GetH_(ref(0.5)))
+
+
+def test_theta_against_independent_quadrature(lib, oracle):
+    """theta_ (camb/theta.cc:296): r_s(a*)/D_A(a*) from its own background run and exact spline integrals, against
+    scipy quadrature of the same integrands over the table arrays_ produced.  100 theta of the config-2 point (a chain
+    best fit) must also land near the measured acoustic scale."""
+    from scipy import integrate
+    lib.theta_.restype = D
+    rc, gm, nm = call_arrays(lib, oracle)
+    assert rc == 0
+    g = oracle.get
+    h0_kms = g("gal_h0") * 2.99792458e8 / 1000
+    ombh2, astar = GAL["ombh2"], 1 / 1090.0
+    th = lib.theta_(ref(g("gal_om")), ref(g("gal_orad")), ref(ombh2), ref(h0_kms), ref(astar), ref(g("gal_c2")), ref(g("gal_c3")),
+                    ref(g("gal_c4")), ref(g("gal_cG")), gm, nm, C.byref(C.c_int(1)))
+    H = lambda a: lib.GetH_(ref(a))
+    rs, _ = integrate.quad(lambda a: 1 / (a * a * H(a) * np.sqrt(3 * (1 + 3e4 * a * ombh2))), 1e-8, astar, epsrel=1e-10, limit=400,
+                           points=[1e-7, 1e-6, 1e-5, 1e-4])
+    da, _ = integrate.quad(lambda a: 1 / (a * a * H(a)), astar, 1.0, epsrel=1e-10, limit=400, points=[0.01, 0.1])
+    assert abs(th / (rs / da) - 1) < 1e-7
+    assert 1.03 < 100 * th < 1.05
+    assert abs(lib.GetH_(ref(1.0)) - 1) < 1e-12  # arrays_' tables untouched by theta_
+    # rejected background -> -1 (camb/theta.cc:380)
+    bad = lib.theta_(ref(g("gal_om")), ref(g("gal_orad")), ref(ombh2), ref(h0_kms), ref(astar), ref(-14.539), ref(-5.73), ref(-1.2),
+                     ref(0.4), gm, nm, C.byref(C.c_int(1)))
+    assert bad == -1.0
