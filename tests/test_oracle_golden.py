@@ -78,6 +78,16 @@ def test_lensed_lcdm_against_reference_theory_cl():
         worst_u = max(worst_u, abs(clu[0, l - 2] / r[1] - 1))
         assert abs(cl[1, l - 2] / r[3] - 1) < 4e-3, (l, cl[1, l - 2], r[3])
     assert worst_l < 1.5e-3 and worst_u > 2e-2, (worst_l, worst_u)
+    # TE changes sign: compare on the local max-norm of 150-multipole windows (one acoustic oscillation)
+    for l0 in range(50, 1500, 150):
+        rr = np.array([ref[ref[:, 0] == l][0][2] for l in range(l0, l0 + 150)])
+        assert np.max(np.abs(cl[3, l0 - 2:l0 + 148] - rr)) < 4e-3 * np.max(np.abs(rr)), l0
+    # lensing potential: the file's PP = [L(L+1)]^2 C_L^phiphi / 2pi, Cl_scalar(:, C_Phi) = L^4 C_L^phiphi
+    # (camb/cmbmain.f90:2231-2260); the linear potential agrees below L ~ 100 where halofit changes nothing
+    for l in (10, 20, 30, 60, 100):
+        r = ref[ref[:, 0] == l][0]
+        pp = o.Cl()[3, l - 2] * ((l + 1.0) / l) ** 2 / (2 * np.pi)
+        assert abs(pp / r[5] - 1) < 6e-3, (l, pp, r[5])
     for l in (100, 500, 1000):  # BB from lensing only; linear vs halofit potential: 5-10% low
         r = ref[ref[:, 0] == l][0]
         assert 0.85 < cl[2, l - 2] / r[4] < 1.0
