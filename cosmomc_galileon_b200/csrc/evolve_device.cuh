@@ -18,6 +18,12 @@
 
 // functions shared with the host-side galileon.cc replacement (csrc/galileon_host.cu)
 #define GC_HD __host__ __device__
+// read-only table rows (thermo, background spline, neutrino tables): global, never written by the kernel
+#ifdef __CUDA_ARCH__
+#define GC_LDG(p) __ldg(p)
+#else
+#define GC_LDG(p) (*(p))
+#endif
 #define GC_LANES 32
 #define GC_NCOL 12  // column 0 = y, columns 1..9 = dverk w(:,1..9), 10 = y of a pending output, 11 = its y'
 
@@ -62,17 +68,23 @@ __device__ inline void thermo(const DevModel& M, double tau, double& cs2b, doubl
   const int nth = M.nthermo;
   if (i >= nth) {
     const double* r = M.th + (size_t)(nth - 1) * 5;
-    cs2b = r[0] + (d + i - nth) * r[1];
-    opacity = r[2] + (d - nth) * r[3];
+    cs2b = GC_LDG(r) + (d + i - nth) * GC_LDG(r + 1);
+    opacity = GC_LDG(r + 2) + (d - nth) * GC_LDG(r + 3);
     if (dopacity) *dopacity = 0;
     return;
   }
   if (i < 1) i = 1;  // reference aborts ("thermo out of bounds"); cannot happen for tau >= tauminn
   const double* r0 = M.th + (size_t)(i - 1) * 5;
   const double* r1 = r0 + 5;
-  cs2b = herm(r0[0], r0[1], r1[0], r1[1], d);
-  opacity = herm(r0[2], r0[3], r1[2], r1[3], d);
-  if (dopacity) *dopacity = herm(r0[3], r0[4], r1[3], r1[4], d) * M.inv_dlntau / tau;
+  double a0[5], a1[5];
+#pragma unroll
+  for (int c = 0; c < 5; c++) {
+    a0[c] = GC_LDG(r0 + c);
+    a1[c] = GC_LDG(r1 + c);
+  }
+  cs2b = herm(a0[0], a0[1], a1[0], a1[1], d);
+  opacity = herm(a0[2], a0[3], a1[2], a1[3], d);
+  if (dopacity) *dopacity = herm(a0[3], a0[4], a1[3], a1[4], d) * M.inv_dlntau / tau;
 }
 
 // camb/modules.f90:2771-2783 via the running-minimum table (same index as the linear scan)
@@ -117,8 +129,8 @@ GC_HD inline void Nu_background(const DevModel& M, double am, double& rhonu, dou
   d = d - i;
   const double* r0 = M.nu_tab + (size_t)(i - 1) * 6;
   const double* r1 = r0 + 6;
-  rhonu = exp(herm(r0[0], r0[1], r1[0], r1[1], d));
-  pnu = exp(herm(r0[2], r0[3], r1[2], r1[3], d));
+  rhonu = exp(herm(GC_LDG(r0 + 0), GC_LDG(r0 + 1), GC_LDG(r1 + 0), GC_LDG(r1 + 1), d));
+  pnu = exp(herm(GC_LDG(r0 + 2), GC_LDG(r0 + 3), GC_LDG(r1 + 2), GC_LDG(r1 + 3), d));
 }
 
 // camb/modules.f90:1790-1817
@@ -130,7 +142,7 @@ GC_HD inline double Nu_drho(const DevModel& M, double am, double adotoa, double 
   d = d - i;
   const double* r0 = M.nu_tab + (size_t)(i - 1) * 6;
   const double* r1 = r0 + 6;
-  return rhonu * adotoa * herm(r0[1], r0[4], r1[1], r1[4], d) / M.dlnam;
+  return rhonu * adotoa * herm(GC_LDG(r0 + 1), GC_LDG(r0 + 4), GC_LDG(r1 + 1), GC_LDG(r1 + 4), d) / M.dlnam;
 }
 
 // camb/modules.f90:1821-1850
@@ -143,7 +155,7 @@ GC_HD inline double Nu_dp(const DevModel& M, double am, double adotoa, double pn
   d = d - i;
   const double* r0 = M.nu_tab + (size_t)(i - 1) * 6;
   const double* r1 = r0 + 6;
-  return pnu * adotoa * herm(r0[3], r0[5], r1[3], r1[5], d) / M.dlnam;
+  return pnu * adotoa * herm(GC_LDG(r0 + 3), GC_LDG(r0 + 5), GC_LDG(r1 + 3), GC_LDG(r1 + 5), d) / M.dlnam;
 }
 
 // Galileon background spline: hbar(a) and x(a)=a*dpi/da from one row search
@@ -161,8 +173,8 @@ __device__ inline void gal_HX(const DevModel& M, double a, double& hbar, double&
   double v0[5], v1[5];
 #pragma unroll
   for (int c = 0; c < 5; c++) {
-    v0[c] = r0[c];
-    v1[c] = r1[c];
+    v0[c] = GC_LDG(r0 + c);
+    v1[c] = GC_LDG(r1 + c);
   }
   if (!(v0[0] <= a && (a < v1[0] || i == n - 2))) {
     while (i > 0 && M.gal[(size_t)i * 5] > a) i--;
