@@ -15,8 +15,11 @@
  *                             DoFlatIntegration :1500)
  *   galcamb_scalar_cls_       CalcScalCls camb/cmbmain.f90:2167 + InterpolateCls :2450
  *   galcamb_set_bessels_      InitSpherBessels / GenerateBessels camb/bessels.f90:34-120
- * Everything before (CAMBParams_Set, init_background, inithermo ...) and after (lensing, file output) stays in
- * the Fortran host; the host hands over the tables it has after InitVars through galcamb_model.
+ *   galcamb_lens_cls_         lens_Cls -> CorrFuncFullSkyImpl camb/lensing.f90:78-528 (post-step, optional)
+ *   galcamb_set_primordial_ + galcamb_transfers_to_powers_   CAMB_TransfersToPowers camb/camb.f90:87-102
+ * Everything before (CAMBParams_Set, inithermo ...) and after (file output) stays in the Fortran host; the host
+ * hands over the tables it has after InitVars through galcamb_model.  The Galileon background itself (arrays_ and
+ * the rest of camb/galileon.cc) has a host-side replacement in the same library: include/galileon_abi.h.
  *
  * Threading: like CAMB itself (camb/cmbmain.f90:7-8) one context = one model batch at a time; call from one
  * host thread per GPU.  Device buffers are owned by the library, host buffers by the caller.
