@@ -167,10 +167,16 @@ def test_lensing_stage_alone_high_l(gpu):
     Cl2[:3] *= 0.6
     Cl3 = Cl.copy()
     Cl3[3] *= 1e3  # lensing potential far too large: error_norm_lensing (camb/lensing.f90:230-235)
-    gpu.set_models([t, t.copy(), t.copy()])
-    for i, c in enumerate((Cl, Cl2, Cl3)):
+    Cl0 = Cl.copy()
+    Cl0[3:] = 0  # no lensing potential: the transform must return the unlensed spectra and no B modes
+    gpu.set_models([t, t.copy(), t.copy(), t.copy()])
+    for i, c in enumerate((Cl, Cl2, Cl3, Cl0)):
         gpu.put_Cls(c, i)
     gpu.lens_Cls()
+    L0 = gpu.Cl_lensed(3)
+    nl = L0.shape[1]
+    assert np.max(np.abs(L0[0] / Cl[0, :nl] - 1)) < 1e-11 and np.max(np.abs(L0[1] / Cl[1, :nl] - 1)) < 1e-11
+    assert np.max(np.abs(L0[2])) < 1e-24 and np.max(np.abs(L0[3] - Cl[2, :nl])) < 1e-11 * np.max(np.abs(Cl[2]))
     L = gpu.Cl_lensed(0)
     check_lensed(L, Lo, TOL_CL)
     np.testing.assert_allclose(gpu.Cl_lensed(1), 0.6 * L, rtol=1e-11)

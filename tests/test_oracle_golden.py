@@ -119,3 +119,11 @@ def test_lensing_golden_and_properties():
     o.put("Cl", Cl2)
     o.stage("lensing")
     np.testing.assert_allclose(o.Cl_lensed(), 1.7 * L, rtol=1e-11)
+    # no lensing potential -> nothing happens: sigma^2 = C_gl,2 = 0, every correlation-function correction vanishes
+    Cl0 = Cl.copy()
+    Cl0[3:] = 0
+    o.put("Cl", Cl0)
+    o.stage("lensing")
+    L0 = o.Cl_lensed()
+    assert np.max(np.abs(L0[0] / Cl[0, :nl] - 1)) < 1e-12 and np.max(np.abs(L0[1] / Cl[1, :nl] - 1)) < 1e-12
+    assert np.max(np.abs(L0[2])) < 1e-25 and np.max(np.abs(L0[3] - Cl[2, :nl])) < 1e-12 * np.max(np.abs(Cl[2]))
