@@ -6,18 +6,19 @@
 // build, link or call anything in oracle/.  The CUDA product in
 // cosmomc_galileon_b200/ never includes or links these files.
 //
-// PARITY STATUS: "parity unpinned" against the real reference binary.  The
-// reference cannot be built in this image (no Fortran compiler, no GSL, Intel-only
-// build) and its tree holds no golden vector for the Galileon
-// hot path.  The oracle is pinned instead by (i) known-answer
-// tests of each numerical primitive (scipy spherical_jn, natural cubic splines,
-// dverk on closed-form ODEs), (ii) the in-code invariants of the reference
-// (Friedmann closure, h(1)=x(1)=1, stability checks), (iii) the one C_l file the
-// reference ships for this path, data/base_plikHM_TT_lowTEB.minimum.theory_cl
-// (LENSED LCDM): with the lensing post-step (orc_lensing.cpp) the oracle's lensed TT
-// agrees with it to < 1.5e-3 at every 10th l in 30..1500, EE to < 4e-3
-// (tests/test_oracle_golden.py).  LCDM only, 1e-3 not 1e-6: still "unpinned" for the
-// Galileon terms.  See DESIGN.md.
+// PARITY STATUS: the Galileon terms are PINNED against the reference's own object code: oracle/Makefile target
+// `ref` compiles the unmodified camb/galileon.cc (where it lies under /root/reference) into oracle/_ref/
+// libgalref.so against stand-in GSL headers (oracle/ref/gsl_shim) and tests/test_oracle_ref.py compares
+// GetdHdX_, grhogal_, gpresgal_, Chigal_, qgal_, Pigal_, dphisecond_, pigalprime_ (1e-13; incl. the hard zero below
+// a = 9.99999e-7, 0/1/3 mass eigenstates) and the whole arrays_ background (bit-identical h(a), x(a), c5 closure)
+// with this restatement.  The FORTRAN part of the path (equations_galileon.f90, cmbmain.f90, modules.f90 ...)
+// cannot be built in this image (no Fortran compiler) and the tree holds no golden vector for
+// the Galileon C_l: that part stays pinned by (i) known-answer tests of each numerical
+// primitive (scipy spherical_jn, natural cubic splines, dverk on closed-form ODEs), (ii) the in-code invariants of
+// the reference (Friedmann closure, h(1)=x(1)=1, stability checks), (iii) the one C_l file the reference ships for
+// this path, data/base_plikHM_TT_lowTEB.minimum.theory_cl (LENSED LCDM): with the lensing post-step
+// (orc_lensing.cpp) the oracle's lensed TT agrees with it to < 1.5e-3 at every 10th l in 30..1500, EE to < 4e-3
+// (tests/test_oracle_golden.py).  See DESIGN.md.
 //
 // Third-party arithmetic not vendored in the reference: GSL (version unpinned;
 // camb/Makefile_main:64).  gsl_odeiv_step_rkf45 + gsl_odeiv_control_y_new and

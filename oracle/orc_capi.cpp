@@ -33,8 +33,14 @@ int orc_set(void* h, const char* name, double v) {
 #undef D
 #undef I
   if (n == "lAccuracyBoost") { P.lAccuracyBoost = (float)v; return 0; }
-  if (n == "Nu_mass_numbers1") { P.Nu_mass_numbers[0] = (int)v; return 0; }
-  if (n == "Nu_mass_fractions1") { P.Nu_mass_fractions[0] = v; return 0; }
+  // per-eigenstate inputs: name + 1-based eigenstate index (camb/inidriver.F90:143-165)
+  if (!n.empty() && n.back() >= '1' && n.back() <= '0' + max_nu) {
+    const int i = n.back() - '1';
+    const std::string b = n.substr(0, n.size() - 1);
+    if (b == "Nu_mass_numbers") { P.Nu_mass_numbers[i] = (int)v; return 0; }
+    if (b == "Nu_mass_fractions") { P.Nu_mass_fractions[i] = v; return 0; }
+    if (b == "Nu_mass_degeneracies") { P.Nu_mass_degeneracies[i] = v; return 0; }
+  }
   return 1;
 }
 
@@ -165,10 +171,15 @@ double orc_get(void* h, const char* name) {
   if (n == "sum_n_trial") return M.cnt.sum_n_trial;
   if (n == "flop_ode") return M.cnt.flop_ode;
   if (n == "n_iter") return M.cnt.n_iter;
-  if (n == "grhormass1") return M.grhormass[1];
-  if (n == "nu_masses1") return M.nu_masses[1];
-  if (n == "nu_tau_nonrelativistic1") return M.nu_tau_nonrelativistic[1];
-  if (n == "nu_tau_massive1") return M.nu_tau_massive[1];
+  if (!n.empty() && n.back() >= '1' && n.back() <= '0' + max_nu) {  // per-eigenstate values, 1-based suffix
+    const int i = n.back() - '0';
+    const std::string b = n.substr(0, n.size() - 1);
+    if (b == "grhormass") return M.grhormass[i];
+    if (b == "nu_masses") return M.nu_masses[i];
+    if (b == "nu_tau_nonrelativistic") return M.nu_tau_nonrelativistic[i];
+    if (b == "nu_tau_massive") return M.nu_tau_massive[i];
+    if (b == "Nu_mass_degeneracies") return M.Nu_mass_degeneracies[i];
+  }
   return NAN;
 }
 
@@ -232,8 +243,8 @@ long orc_get_array(void* h, const char* name, double* out, long cap) {
   } else if (n == "nu_int_kernel") {
     for (int i = 1; i <= M.nu.nqmax; i++) tmp.push_back(M.nu.nu_int_kernel[i]);
     v = &tmp;
-  } else if (n == "nu_tau_notmassless1") {
-    for (int i = 1; i <= M.nu.nqmax; i++) tmp.push_back(M.nu_tau_notmassless[i][1]);
+  } else if (n.rfind("nu_tau_notmassless", 0) == 0 && n.size() == 19 && n.back() >= '1' && n.back() <= '0' + max_nu) {
+    for (int i = 1; i <= M.nu.nqmax; i++) tmp.push_back(M.nu_tau_notmassless[i][n.back() - '0']);
     v = &tmp;
   } else if (n == "regions_tau" || n == "regions_bess") {
     // flattened region table: per region {Low, High, delta, start_index, IsLog}

@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE.  Empty stand-in: camb/galileon.cc includes <gsl/gsl_integration.h> but uses nothing from it.
+#pragma once
+#include <cmath>
