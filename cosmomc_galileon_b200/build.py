@@ -13,8 +13,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "libgalcamb_b200.so")
+# GALCAMB_VARIANT=<name> builds an experiment variant next to the product library (own object directory,
+# libgalcamb_b200_<name>.so); select it at run time with GALCAMB_LIB=<path>
+VARIANT = os.environ.get("GALCAMB_VARIANT", "")
+OBJ = os.path.join(HERE, "_build" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "libgalcamb_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 SOURCES = ["evolve.cu", "los.cu", "lensing.cu", "capi.cu", "fp64_peak.cu", "galileon_host.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FMAD = os.environ.get("GALCAMB_FMAD", "true")

@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-MAX_NU, MAX_NQ, MAX_REGIONS = 3, 5, 16
+MAX_NU, MAX_NQ, MAX_REGIONS = 5, 5, 16
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 

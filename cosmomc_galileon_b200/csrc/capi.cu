@@ -18,7 +18,8 @@
 #include "model.h"
 
 extern "C" void gc_upload_constants();
-extern "C" cudaError_t gc_launch_evolve(const DevModel*, const int2*, int, double*, int, int*, unsigned long long*, cudaStream_t);
+extern "C" cudaError_t gc_launch_evolve(const DevModel*, const int2*, int, int, int, unsigned*, int*, unsigned long long*, cudaStream_t);
+extern "C" int gc_evolve_warps_per_cta(int);
 extern "C" cudaError_t gc_set_bess_regions(const GcRegions*);
 extern "C" cudaError_t gc_launch_bessels(double2*, const double*, const int*, double*, int, int, cudaStream_t);
 extern "C" cudaError_t gc_launch_spline_k(const DevModel*, int, int, cudaStream_t);
@@ -85,19 +86,20 @@ struct Ctx {
   double* d_nu_tab = nullptr;
   bool nu_tab_set = false;
   // batch
-  std::vector<Slot> slots;
+  std::vector<Slot> slots;  // the slots of the current batch
+  std::vector<Slot> spare;  // slots of earlier, larger batches: their device tables / pinned staging are reused, not leaked
   DevModel* d_models = nullptr;
   size_t models_cap = 0;
   int2* d_items = nullptr;
   size_t items_cap = 0;
   int* d_status = nullptr;
-  double* d_ws = nullptr;
-  size_t ws_cap = 0;
+  unsigned* d_queue = nullptr;  // work-queue head of the per-k kernel
+  int num_sms = 0;
   unsigned long long* d_counters = nullptr;  // [0..2] evolve, [3] n_iter
   std::vector<int2> items;
   double ms[8] = {0};
   double counters[4] = {0};
-  double evolve_stats[2] = {0};
+  double evolve_stats[3] = {0};
   std::string err;
 };
 
@@ -212,7 +214,9 @@ int galcamb_init_(const int* device) {
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   for (auto& e : g.ev) CK(cudaEventCreate(&e));
   gc_upload_constants();
-  CK(cudaMalloc((void**)&g.d_counters, 8 * sizeof(unsigned long long)));
+  CK(cudaMalloc((void**)&g.d_counters, 24 * sizeof(unsigned long long)));
+  CK(cudaMalloc((void**)&g.d_queue, sizeof(unsigned)));
+  CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, g.device));
   CK(cudaMalloc((void**)&g.d_nu_tab, (size_t)GC_NRHOPN * 6 * sizeof(double)));
   CK(cudaDeviceSetLimit(cudaLimitStackSize, 8192));
   g.ready = true;
@@ -223,14 +227,16 @@ void galcamb_free_(void) {
   if (!g.ready) return;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
-  for (auto& s : g.slots) {
-    if (s.d_tables) cudaFree(s.d_tables);
-    if (s.d_out) cudaFree(s.d_out);
-    if (s.staging) cudaFreeHost(s.staging);
+  for (auto* v : {&g.slots, &g.spare}) {
+    for (auto& s : *v) {
+      if (s.d_tables) cudaFree(s.d_tables);
+      if (s.d_out) cudaFree(s.d_out);
+      if (s.staging) cudaFreeHost(s.staging);
+    }
+    v->clear();
   }
-  g.slots.clear();
   for (void* p : {(void*)g.d_ls, (void*)g.d_xs, (void*)g.d_bess, (void*)g.d_tmpl, (void*)g.d_nu_tab, (void*)g.d_models,
-                  (void*)g.d_items, (void*)g.d_status, (void*)g.d_ws, (void*)g.d_counters, (void*)g.d_tmpl_pp, (void*)g.d_lens_ta,
+                  (void*)g.d_items, (void*)g.d_status, (void*)g.d_queue, (void*)g.d_counters, (void*)g.d_tmpl_pp, (void*)g.d_lens_ta,
                   (void*)g.d_lens_tb, (void*)g.d_lens_cin, (void*)g.d_lens_apod, (void*)g.d_lens_partial, (void*)g.d_lensed,
                   (void*)g.d_lens_status})
     if (p) cudaFree(p);
@@ -328,11 +334,21 @@ int galcamb_set_lensing_template_(const double* pp, const int* lmax_tmpl) {
 int galcamb_batch_begin_(const int* nmodels) {
   if (!g.ready) return fail(100, "not initialised");
   if (*nmodels < 1) return fail(5, "nmodels < 1");
-  if ((int)g.slots.size() < *nmodels) g.slots.resize(*nmodels);
+  // only nmodels slots take part; slots a smaller batch does not use are parked (with their buffers), not dropped
+  while ((int)g.slots.size() > *nmodels) {
+    g.spare.push_back(g.slots.back());
+    g.slots.pop_back();
+  }
+  while ((int)g.slots.size() < *nmodels) {
+    if (!g.spare.empty()) {
+      g.slots.push_back(g.spare.back());
+      g.spare.pop_back();
+    } else {
+      g.slots.emplace_back();
+    }
+  }
   for (auto& s : g.slots) s.set = false;
   g.items.clear();
-  // only the first nmodels slots take part
-  g.slots.resize(*nmodels);
   return 0;
 }
 
@@ -524,64 +540,83 @@ int galcamb_evolve_sources_(void) {
     const int nv = std::max(nvA, nvB);
     NV = std::max(NV, nv);
   }
+  // Work queue of the per-k kernel: groups of GC_IPW = 4 items, one group per warp at a time.  Ordered by k index
+  // ascending -- low k first: those modes are integrated all the way to tau0 (~7600 trial steps) while
+  // k*tau > max_etak_scalar stops the high-k modes at ~800 (camb/cmbmain.f90:1034), so the longest items start
+  // first and the short ones back-fill (the reference's SCHEDULE(DYNAMIC) over k, camb/cmbmain.f90:201).  A group
+  // holds the SAME k index of up to four cosmologies (near-identical control flow across the warp).  With few
+  // items (a single model: ~200) a group holds fewer items so that every item gets a warp of its own.
+  const int NVP = NV;
+  const int warps_per_sm = gc_evolve_warps_per_cta(NVP);
+  if (warps_per_sm < 1) return fail(5, "state vector too long for the shared memory of one SM");
+  long total_items = 0;
+  for (auto& s : g.slots) total_items += s.host.nk;
+  const long slots_hw = (long)g.num_sms * warps_per_sm;
+  int ipw = (int)((total_items + slots_hw - 1) / slots_hw);
+  ipw = std::max(1, std::min(ipw, 4));
+  if (const char* e = getenv("GALCAMB_ITEMS_PER_WARP")) ipw = std::max(1, std::min(atoi(e), 4));  // experiment knob
   g.items.clear();
-  static int order = -1;
-  if (order < 0) {
-    const char* e = getenv("GALCAMB_ITEM_ORDER");  // 0: (k, model) lanes = cosmologies at one k ; 1: (model, k) lanes = adjacent k
-    order = e ? atoi(e) : 0;
-  }
-  if (order == 0) {
-    // every k index starts on a warp boundary (padding items have model = -1): a warp never mixes different k, whose
-    // step sequences and switch times differ -- mixing them costs 2-4x (a single model is 197 one-lane warps)
-    for (int kk = 0; kk < max_nk; kk++) {
-      for (int m = 0; m < nm; m++)
-        if (kk < g.slots[m].host.nk) g.items.push_back(make_int2(m, kk));
-      while (g.items.size() % 32) g.items.push_back(make_int2(-1, -1));
+  for (int kk = 0; kk < max_nk; kk++) {
+    int in_group = 0;
+    for (int m = 0; m < nm; m++) {
+      if (kk >= g.slots[m].host.nk) continue;
+      g.items.push_back(make_int2(m, kk));
+      if (++in_group == ipw) {
+        for (; in_group < 4; in_group++) g.items.push_back(make_int2(-1, -1));
+        in_group = 0;
+      }
     }
-  } else {
-    // warps of 32 adjacent k of ONE model (constants warp-uniform), dealt low-k-first across models
-    for (int k0 = 0; k0 < max_nk; k0 += 32)
-      for (int m = 0; m < nm; m++)
-        for (int kk = k0; kk < std::min(k0 + 32, g.slots[m].host.nk); kk++) g.items.push_back(make_int2(m, kk));
+    if (in_group)
+      for (; in_group < 4; in_group++) g.items.push_back(make_int2(-1, -1));
   }
   const int nitems = (int)g.items.size();
+  const int ngroups = nitems / 4;
   if ((size_t)nitems > g.items_cap) {
     if (g.d_items) cudaFree(g.d_items);
     if (g.d_status) cudaFree(g.d_status);
+    g.d_items = nullptr;
+    g.d_status = nullptr;
+    g.items_cap = 0;
     CK(cudaMalloc((void**)&g.d_items, nitems * sizeof(int2)));
     CK(cudaMalloc((void**)&g.d_status, nitems * sizeof(int)));
     g.items_cap = nitems;
   }
-  const size_t nwarps = (nitems + 31) / 32;
-  const size_t ws_need = nwarps * 12 * (size_t)NV * 32;  // GC_NCOL columns (csrc/evolve_device.cuh)
-  if (grow(&g.d_ws, &g.ws_cap, ws_need)) return fail(100, "cudaMalloc workspace");
   CK(cudaMemcpyAsync(g.d_items, g.items.data(), nitems * sizeof(int2), cudaMemcpyHostToDevice, g.stream));
-  CK(cudaMemsetAsync(g.d_counters, 0, 8 * sizeof(unsigned long long), g.stream));
+  CK(cudaMemsetAsync(g.d_counters, 0, 24 * sizeof(unsigned long long), g.stream));
   CK(cudaEventRecord(g.ev[0], g.stream));
-  CK(gc_launch_evolve(g.d_models, g.d_items, nitems, g.d_ws, NV, g.d_status, g.d_counters, g.stream));
+  CK(gc_launch_evolve(g.d_models, g.d_items, ngroups, NVP, g.num_sms, g.d_queue, g.d_status, g.d_counters, g.stream));
   CK(cudaEventRecord(g.ev[1], g.stream));
   std::vector<int> st(nitems);
   CK(cudaMemcpyAsync(st.data(), g.d_status, nitems * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-  unsigned long long c[8];
-  CK(cudaMemcpyAsync(c, g.d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
+  unsigned long long c[24];
+  CK(cudaMemcpyAsync(c, g.d_counters, 24 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]);
   g.ms[0] = ms;
-  // c[0] counts the evaluations executed; the reference algorithm also evaluates y' once per output
-  // (camb/equations_galileon.f90:1297), which K1 takes from the next step's k1 (c[4] outputs): the algorithmic
-  // count of SURVEY.md section 8d is their sum
-  g.counters[0] = (double)(c[0] + c[4]);
+  // c[0] = right-hand-side evaluations of the reference algorithm: k1..k8 of every trial step
+  // (k1 not after a rejected one) + one per output (camb/equations_galileon.f90:1297).  K1 executes c[5] of them:
+  // the y' of an output is the k1 of the next step (c[4] outputs served that way), a rejected step re-forms its k1.
+  g.counters[0] = (double)c[0];
   g.counters[1] = (double)c[1];
   g.counters[2] = (double)c[2];
-  g.evolve_stats[0] = (double)c[0];
+  g.evolve_stats[0] = (double)c[5];
   g.evolve_stats[1] = (double)c[4];
-  if (getenv("GALCAMB_PHASE_PROFILE"))  // only meaningful for a -DGC_PROFILE_PHASES build: warp-cycles per phase
-    fprintf(stderr, "[galcamb] warp-cycles: advance %.3e combine %.3e flush+loop %.3e barrier+derivs %.3e\n", (double)c[5],
-            (double)c[6], (double)c[3], (double)c[7]);
+  g.evolve_stats[2] = (double)c[6];
+  if (getenv("GALCAMB_PHASE_PROFILE")) {  // only meaningful for a -DGC_PROFILE_PHASES build: warp-cycles per phase
+    const char* nm[9] = {"window", "phaseA", "phaseB", "combine", "scalar", "hier", "output", "final", "advance"};
+    double tot = 0;
+    for (int i = 0; i < 9; i++) tot += (double)c[8 + i];
+    fprintf(stderr, "[galcamb] warp-cycles per trial step (%.0f trial steps, %d items per warp):", (double)c[6], ipw);
+    for (int i = 0; i < 9; i++)
+      fprintf(stderr, " %s %.0f (%.1f%%)", nm[i], (double)c[8 + i] / ((double)c[6] / ipw), 100.0 * c[8 + i] / tot);
+    fprintf(stderr, "\n");
+  }
   int rc = 0;
   for (int i = 0; i < nitems; i++)
     if (st[i] && g.items[i].x >= 0) {
+      // dverk's own failure codes (101: bad re-entry, 102: hmin > hmax, 103: more equations than the kernel was sized
+      // for) all surface as CAMB's error_evolution (camb/equations_galileon.f90:285-292); the raw code stays in the message
       g.slots[g.items[i].x].status = st[i] >= 100 ? 4 : st[i];
       rc = 4;  // error_evolution
       char buf[160];
@@ -873,8 +908,8 @@ int galcamb_get_timings_(double* ms) {
 }
 
 int galcamb_get_evolve_stats_(double* s) {
-  s[0] = g.evolve_stats[0];
-  s[1] = g.evolve_stats[1];
+  s[0] = g.evolve_stats[0];  // right-hand sides executed
+  s[1] = g.evolve_stats[1];  // outputs that took their y' from the next step's k1
   return 0;
 }
 

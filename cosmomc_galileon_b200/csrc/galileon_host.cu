@@ -457,12 +457,21 @@ double GetH_(double* point) {
   return spline_eval(G.a, G.h, G.ch, *point);
 }
 
+// the closed forms below are the ones the device evaluates (galileon_fast.cuh): one background record for given
+// (a, H = a*hbar, x, dh, dx), then the term as a linear form in the perturbations
+static gc::GalConst host_const() { return gc::GalConst{G.M.c2, G.M.c3, G.M.c4, G.M.c5, G.M.cG, G.M.h0, G.M.orad}; }
+static double host_lam_nu(const double* pnu) {
+  double lam = 0;
+  for (int i = 0; i < G.M.n_eig; i++) lam += G.M.grhormass[i] * pnu[i];
+  return lam;
+}
+
 void GetdHdX_(double* point, double* hcamb, double* xcamb, double& dh, double& dx, double* grhormass, double* nu_masses,
               int* nu_mass_eigenstates) {
   (void)grhormass; (void)nu_masses; (void)nu_mass_eigenstates;  // the values given to arrays_ are in use
   double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
   nu_pressures(*point, rhonu, pnu);
-  gc::gal_GetdHdX(G.M, *point, *hcamb, *xcamb, pnu, dh, dx);
+  gc::gal_fast_dhdx(host_const(), *point, *hcamb / *point, *xcamb, host_lam_nu(pnu), dh, dx);
 }
 
 double ct_(double* point, double* grhormass, double* nu_masses, int* nu_mass_eigenstates) {
@@ -474,30 +483,48 @@ double ct_(double* point, double* grhormass, double* nu_masses, int* nu_mass_eig
                    (0.5 - 0.75 * c4 * prod4 + 1.5 * c5 * prod5 * h + 0.5 * cG * prod2));
 }
 
-double grhogal_(double* point, double* hcamb, double* xcamb) { return gc::gal_grhogal(G.M, *point, *hcamb, *xcamb); }
+static void host_fill(double a, double hc, double x, double dh, double dx, double k, gc::GalFast& F) {
+  gc::gal_fast_fill(host_const(), a, hc / a, x, dh, dx, k, F);
+}
+
+double grhogal_(double* point, double* hcamb, double* xcamb) {
+  gc::GalFast F;
+  host_fill(*point, *hcamb, *xcamb, 0, 0, 1, F);
+  return F.grhogal;
+}
 
 double gpresgal_(double* point, double* hcamb, double* xcamb, double* dhcamb, double* dxcamb) {
-  return gc::gal_gpresgal(G.M, *point, *hcamb, *xcamb, *dhcamb, *dxcamb);
+  gc::GalFast F;
+  host_fill(*point, *hcamb, *xcamb, *dhcamb, *dxcamb, 1, F);
+  return F.gpresgal;
 }
 
 double Chigal_(double* point, double* hcamb, double* xcamb, double* dgrho, double* eta, double* dphi, double* dphiprime,
                double* k) {
-  return gc::gal_Chigal(G.M, *point, *hcamb, *xcamb, *dgrho, *eta, *dphi, *dphiprime, *k);
+  gc::GalFast F;
+  host_fill(*point, *hcamb, *xcamb, 0, 0, *k, F);
+  return gc::gal_fast_Chigal(F, *dgrho, *eta, *dphi, *dphiprime);
 }
 
 double qgal_(double* point, double* hcamb, double* xcamb, double* dgq, double* eta, double* dphi, double* dphiprime, double* k) {
-  return gc::gal_qgal(G.M, *point, *hcamb, *xcamb, *dgq, *eta, *dphi, *dphiprime, *k);
+  (void)eta;
+  gc::GalFast F;
+  host_fill(*point, *hcamb, *xcamb, 0, 0, *k, F);
+  return gc::gal_fast_qgal(F, *dgq, *dphi, *dphiprime);
 }
 
 double Pigal_(double* point, double* hcamb, double* xcamb, double* dhcamb, double* dxcamb, double* dgrho, double* dgq,
               double* dgpi, double* eta, double* dphi, double* k) {
-  return gc::gal_Pigal(G.M, *point, *hcamb, *xcamb, *dhcamb, *dxcamb, *dgrho, *dgq, *dgpi, *eta, *dphi, *k);
+  gc::GalFast F;
+  host_fill(*point, *hcamb, *xcamb, *dhcamb, *dxcamb, *k, F);
+  return gc::gal_fast_Pigal(host_const(), F, *dgrho, *dgq, *dgpi, *eta, *dphi);
 }
 
 double dphisecond_(double* point, double* hcamb, double* xcamb, double* dhcamb, double* dxcamb, double* dgrho, double* dgq,
                    double* eta, double* dphi, double* dphiprime, double* k, double* deltafprime) {
-  return gc::gal_dphisecond(G.M, *point, *hcamb, *xcamb, *dhcamb, *dxcamb, *dgrho, *dgq, *eta, *dphi, *dphiprime, *k,
-                            *deltafprime);
+  gc::GalFast F;
+  host_fill(*point, *hcamb, *xcamb, *dhcamb, *dxcamb, *k, F);
+  return gc::gal_fast_dphisecond(host_const(), F, *dgrho, *dgq, *eta, *dphi, *dphiprime, *deltafprime);
 }
 
 double pigalprime_(double* point, double* hcamb, double* xcamb, double* dhcamb, double* dxcamb, double* dgrho, double* dgq,
@@ -506,8 +533,20 @@ double pigalprime_(double* point, double* hcamb, double* xcamb, double* dhcamb, 
   (void)grhormass; (void)nu_masses; (void)nu_mass_eigenstates;
   double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
   nu_pressures(*point, rhonu, pnu);
-  return gc::gal_pigalprime(G.M, *point, *hcamb, *xcamb, *dhcamb, *dxcamb, *dgrho, *dgq, *dgpi, *pidot, *eta, *dphi,
-                            *dphiprime, *k, *grho, *gpres, pnu);
+  const double a = *point, hc = *hcamb;
+  // the six polynomials of the background system are re-formed from (a, H, x) as the reference does (:1105-1110);
+  // dh and dx are the caller's
+  gc::GalDyn B;
+  double dh_own, dx_own;
+  gc::gal_fast_dhdx(host_const(), a, hc / a, *xcamb, host_lam_nu(pnu), dh_own, dx_own, &B);
+  gc::GalFast F;
+  host_fill(a, hc, *xcamb, *dhcamb, *dxcamb, *k, F);
+  double lam_nu_prime = 0;
+  for (int i = 0; i < G.M.n_eig; i++)
+    lam_nu_prime += G.M.grhormass[i] * (gc::Nu_dp(G.M, a * G.M.nu_masses[i], hc, pnu[i]) - 4 * pnu[i] * hc);
+  gc::GalPiDotLin L;
+  gc::gal_fast_pigalprime_lin(host_const(), F, B, lam_nu_prime, *grho + *gpres, L);
+  return L.p * *dphiprime + L.d * *dphi + L.pid * *pidot + L.g * *dgrho + L.q * *dgq + L.pi * *dgpi + L.e * *eta;
 }
 
 }  // extern "C"

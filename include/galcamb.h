@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GALCAMB_MAX_NU 3
+#define GALCAMB_MAX_NU 5 /* = max_nu, camb/modules.f90:63 */
 #define GALCAMB_MAX_NQ 5
 #define GALCAMB_MAX_REGIONS 16
 

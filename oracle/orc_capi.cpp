@@ -341,6 +341,7 @@ void orc_thermo(void* h, double tau, double* cs2, double* opac, double* dopac) {
 void orc_nu_background(void* h, double am, double* rho, double* p) { Nu_background(*(Model*)h, am, *rho, *p); }
 // all Galileon perturbation terms at one point: out[0..8] = dh, dx, grhogal, gpresgal, Chigal, qgal, Pigal,
 // dphisecond, pigalprime
+double orc_nu_dp(void* h, double am, double adotoa, double pnu) { return Nu_dp(*(Model*)h, am, adotoa, pnu); }
 void orc_gal_terms(void* h, const double* in /*a,dgrho,dgq,dgpi,eta,dphi,dphip,k,deltafprime,pidot,grho,gpres*/,
                    double* out) {
   Model& M = *(Model*)h;

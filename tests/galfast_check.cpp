@@ -10,6 +10,7 @@ extern "C" {
 void* orc_new(); int orc_set(void*, const char*, double); void orc_set_physical(void*, double,double,double,double);
 int orc_stage_background(void*); double orc_get(void*, const char*); double orc_gal_H(void*, double); double orc_gal_X(void*, double);
 void orc_gal_terms(void*, const double*, double*); void orc_nu_background(void*, double, double*, double*);
+double orc_nu_dp(void*, double, double, double);
 }
 int main() {
   void* h = orc_new();
@@ -19,7 +20,7 @@ int main() {
   if (orc_stage_background(h)) { printf("bg fail\n"); return 1; }
   gc::GalConst G{orc_get(h,"gal_c2"), orc_get(h,"gal_c3"), orc_get(h,"gal_c4"), orc_get(h,"gal_c5"), orc_get(h,"gal_cG"), orc_get(h,"gal_h0"), orc_get(h,"gal_orad")};
   const double grhormass = orc_get(h, "grhormass1"), numass = orc_get(h, "nu_masses1");
-  double worst[8] = {0};
+  double worst[9] = {0};
   srand(1);
   for (int t = 0; t < 20000; t++) {
     double u = rand() / (double)RAND_MAX;
@@ -32,16 +33,21 @@ int main() {
     double hbar = orc_gal_H(h, a), X = orc_gal_X(h, a), rho, p;
     orc_nu_background(h, a * numass, &rho, &p);
     gc::GalFast F;
-    gc::gal_fast_background(G, a, hbar, X, grhormass * p, k, F);
-    double got[8] = {F.dh, F.dx, F.grhogal, F.gpresgal, gc::gal_fast_Chigal(F, in[1], in[4], in[5], in[6]), gc::gal_fast_qgal(F, in[2], in[5], in[6]),
-                     gc::gal_fast_Pigal(G, F, in[1], in[2], in[3], in[4], in[5]), gc::gal_fast_dphisecond(G, F, in[1], in[2], in[4], in[5], in[6], in[8])};
-    for (int i = 0; i < 8; i++) {
+    gc::GalDyn B;
+    gc::gal_fast_background(G, a, hbar, X, grhormass * p, k, F, &B);
+    gc::GalPiDotLin L;
+    const double Hc = a * hbar;
+    gc::gal_fast_pigalprime_lin(G, F, B, grhormass * (orc_nu_dp(h, a * numass, Hc, p) - 4 * p * Hc), in[10] + in[11], L);
+    const double pigalprime = L.p * in[6] + L.d * in[5] + L.pid * in[9] + L.g * in[1] + L.q * in[2] + L.pi * in[3] + L.e * in[4];
+    double got[9] = {F.dh, F.dx, F.grhogal, F.gpresgal, gc::gal_fast_Chigal(F, in[1], in[4], in[5], in[6]), gc::gal_fast_qgal(F, in[2], in[5], in[6]),
+                     gc::gal_fast_Pigal(G, F, in[1], in[2], in[3], in[4], in[5]), gc::gal_fast_dphisecond(G, F, in[1], in[2], in[4], in[5], in[6], in[8]), pigalprime};
+    for (int i = 0; i < 9; i++) {
       double e = std::fabs(got[i] - ref[i]) / (std::fabs(ref[i]) + 1e-300);
       if (ref[i] == 0 && got[i] == 0) e = 0;
       if (e > worst[i]) worst[i] = e;
     }
   }
-  const char* names[8] = {"dh", "dx", "grhogal", "gpresgal", "Chigal", "qgal", "Pigal", "dphisecond"};
-  for (int i = 0; i < 8; i++) printf("%-10s worst rel err %.3e\n", names[i], worst[i]);
+  const char* names[9] = {"dh", "dx", "grhogal", "gpresgal", "Chigal", "qgal", "Pigal", "dphisecond", "pigalprime"};
+  for (int i = 0; i < 9; i++) printf("%-10s worst rel err %.3e\n", names[i], worst[i]);
   return 0;
 }
