@@ -20,6 +20,8 @@
 extern "C" void gc_upload_constants();
 extern "C" cudaError_t gc_launch_evolve(const DevModel*, const int2*, int, int, int, unsigned*, int*, unsigned long long*, cudaStream_t);
 extern "C" int gc_evolve_warps_per_cta(int);
+extern "C" void gc_upload_constants_batch();
+extern "C" cudaError_t gc_launch_evolve_batch(const DevModel*, const int2*, int, double*, int, int*, unsigned long long*, cudaStream_t);
 extern "C" cudaError_t gc_set_bess_regions(const GcRegions*);
 extern "C" cudaError_t gc_launch_bessels(double2*, const double*, const int*, double*, int, int, cudaStream_t);
 extern "C" cudaError_t gc_launch_spline_k(const DevModel*, int, int, cudaStream_t);
@@ -93,7 +95,10 @@ struct Ctx {
   int2* d_items = nullptr;
   size_t items_cap = 0;
   int* d_status = nullptr;
-  unsigned* d_queue = nullptr;  // work-queue head of the per-k kernel
+  unsigned* d_queue = nullptr;  // work-queue head of the per-k kernel (eight-lane form)
+  double* d_ws = nullptr;       // integrator workspace of the lane-per-item form (large batches)
+  size_t ws_cap = 0;
+  int k1_form = 0;              // which form of K1 the last call used: 0 = eight lanes per item, 1 = lane per item
   int num_sms = 0;
   unsigned long long* d_counters = nullptr;  // [0..2] evolve, [3] n_iter
   std::vector<int2> items;
@@ -214,6 +219,7 @@ int galcamb_init_(const int* device) {
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   for (auto& e : g.ev) CK(cudaEventCreate(&e));
   gc_upload_constants();
+  gc_upload_constants_batch();
   CK(cudaMalloc((void**)&g.d_counters, 24 * sizeof(unsigned long long)));
   CK(cudaMalloc((void**)&g.d_queue, sizeof(unsigned)));
   CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, g.device));
@@ -236,7 +242,7 @@ void galcamb_free_(void) {
     v->clear();
   }
   for (void* p : {(void*)g.d_ls, (void*)g.d_xs, (void*)g.d_bess, (void*)g.d_tmpl, (void*)g.d_nu_tab, (void*)g.d_models,
-                  (void*)g.d_items, (void*)g.d_status, (void*)g.d_queue, (void*)g.d_counters, (void*)g.d_tmpl_pp, (void*)g.d_lens_ta,
+                  (void*)g.d_items, (void*)g.d_status, (void*)g.d_queue, (void*)g.d_ws, (void*)g.d_counters, (void*)g.d_tmpl_pp, (void*)g.d_lens_ta,
                   (void*)g.d_lens_tb, (void*)g.d_lens_cin, (void*)g.d_lens_apod, (void*)g.d_lens_partial, (void*)g.d_lensed,
                   (void*)g.d_lens_status})
     if (p) cudaFree(p);
@@ -540,34 +546,58 @@ int galcamb_evolve_sources_(void) {
     const int nv = std::max(nvA, nvB);
     NV = std::max(NV, nv);
   }
-  // Work queue of the per-k kernel: groups of GC_IPW = 4 items, one group per warp at a time.  Ordered by k index
-  // ascending -- low k first: those modes are integrated all the way to tau0 (~7600 trial steps) while
-  // k*tau > max_etak_scalar stops the high-k modes at ~800 (camb/cmbmain.f90:1034), so the longest items start
-  // first and the short ones back-fill (the reference's SCHEDULE(DYNAMIC) over k, camb/cmbmain.f90:201).  A group
-  // holds the SAME k index of up to four cosmologies (near-identical control flow across the warp).  With few
-  // items (a single model: ~200) a group holds fewer items so that every item gets a warp of its own.
-  const int NVP = NV;
-  const int warps_per_sm = gc_evolve_warps_per_cta(NVP);
-  if (warps_per_sm < 1) return fail(5, "state vector too long for the shared memory of one SM");
+  // Two forms of K1 (DESIGN.md "K1"):
+  //  * eight lanes per item, integrator state in shared memory (csrc/evolve.cu): lowest time per trial step, but an SM
+  //    holds only ~20 items -- the choice while the batch is small enough that the critical path of the slowest k mode
+  //    sets the run time (single spectra, MCMC chain steps, k-sharded calls);
+  //  * one lane per item, state in a lane-interleaved L2/HBM workspace (csrc/evolve_batch.cu): 256 items per SM and
+  //    every lane busy in the scalar part of the right-hand side -- the choice for large parameter batches.
+  // Measured crossover on config 2: ~100 models (20 000 items; 48 models 1.12 s vs 128 models 1.81 s).
   long total_items = 0;
   for (auto& s : g.slots) total_items += s.host.nk;
-  const long slots_hw = (long)g.num_sms * warps_per_sm;
-  int ipw = (int)((total_items + slots_hw - 1) / slots_hw);
-  ipw = std::max(1, std::min(ipw, 4));
-  if (const char* e = getenv("GALCAMB_ITEMS_PER_WARP")) ipw = std::max(1, std::min(atoi(e), 4));  // experiment knob
+  static long octet_items = -1;
+  if (octet_items < 0) {
+    const char* e = getenv("GALCAMB_OCTET_ITEMS");  // experiment knob: item count up to which the eight-lane form is used
+    octet_items = e ? atol(e) : 20000;
+  }
+  const int NVP = NV;
+  const int warps_per_sm = gc_evolve_warps_per_cta(NVP);
+  const bool batch_form = total_items > octet_items || warps_per_sm < 1;
+  g.k1_form = batch_form ? 1 : 0;
   g.items.clear();
-  for (int kk = 0; kk < max_nk; kk++) {
-    int in_group = 0;
-    for (int m = 0; m < nm; m++) {
-      if (kk >= g.slots[m].host.nk) continue;
-      g.items.push_back(make_int2(m, kk));
-      if (++in_group == ipw) {
-        for (; in_group < 4; in_group++) g.items.push_back(make_int2(-1, -1));
-        in_group = 0;
-      }
+  int ipw = 4;
+  if (batch_form) {
+    // every k index starts on a warp boundary (padding items have model = -1): a warp never mixes different k, whose
+    // step sequences and switch times differ -- mixing them costs 2-4x.  Low k first: those modes are integrated all the
+    // way to tau0 (~7600 trial steps) while k*tau > max_etak_scalar stops the high-k modes at ~800
+    // (camb/cmbmain.f90:1034), so the longest items start first and the short ones back-fill the SMs.
+    for (int kk = 0; kk < max_nk; kk++) {
+      for (int m = 0; m < nm; m++)
+        if (kk < g.slots[m].host.nk) g.items.push_back(make_int2(m, kk));
+      while (g.items.size() % 32) g.items.push_back(make_int2(-1, -1));
     }
-    if (in_group)
-      for (; in_group < 4; in_group++) g.items.push_back(make_int2(-1, -1));
+  } else {
+    // Work queue: groups of GC_IPW = 4 items, one group per warp at a time, ordered by k index ascending (longest
+    // first, the reference's SCHEDULE(DYNAMIC) over k, camb/cmbmain.f90:201).  A group holds the SAME k index of up to
+    // four cosmologies (near-identical control flow across the warp).  With few items (a single model: ~200) a group
+    // holds fewer items so that every item gets a warp of its own.
+    const long slots_hw = (long)g.num_sms * warps_per_sm;
+    ipw = (int)((total_items + slots_hw - 1) / slots_hw);
+    ipw = std::max(1, std::min(ipw, 4));
+    if (const char* e = getenv("GALCAMB_ITEMS_PER_WARP")) ipw = std::max(1, std::min(atoi(e), 4));  // experiment knob
+    for (int kk = 0; kk < max_nk; kk++) {
+      int in_group = 0;
+      for (int m = 0; m < nm; m++) {
+        if (kk >= g.slots[m].host.nk) continue;
+        g.items.push_back(make_int2(m, kk));
+        if (++in_group == ipw) {
+          for (; in_group < 4; in_group++) g.items.push_back(make_int2(-1, -1));
+          in_group = 0;
+        }
+      }
+      if (in_group)
+        for (; in_group < 4; in_group++) g.items.push_back(make_int2(-1, -1));
+    }
   }
   const int nitems = (int)g.items.size();
   const int ngroups = nitems / 4;
@@ -583,8 +613,17 @@ int galcamb_evolve_sources_(void) {
   }
   CK(cudaMemcpyAsync(g.d_items, g.items.data(), nitems * sizeof(int2), cudaMemcpyHostToDevice, g.stream));
   CK(cudaMemsetAsync(g.d_counters, 0, 24 * sizeof(unsigned long long), g.stream));
+  if (batch_form) {
+    const size_t nwarps = (nitems + 31) / 32;
+    const size_t ws_need = nwarps * 12 * (size_t)NV * 32;  // GC_NCOL columns (csrc/evolve_batch.cu)
+    if (grow(&g.d_ws, &g.ws_cap, ws_need)) return fail(100, "cudaMalloc workspace");
+  }
   CK(cudaEventRecord(g.ev[0], g.stream));
-  CK(gc_launch_evolve(g.d_models, g.d_items, ngroups, NVP, g.num_sms, g.d_queue, g.d_status, g.d_counters, g.stream));
+  if (batch_form) {
+    CK(gc_launch_evolve_batch(g.d_models, g.d_items, nitems, g.d_ws, NV, g.d_status, g.d_counters, g.stream));
+  } else {
+    CK(gc_launch_evolve(g.d_models, g.d_items, ngroups, NVP, g.num_sms, g.d_queue, g.d_status, g.d_counters, g.stream));
+  }
   CK(cudaEventRecord(g.ev[1], g.stream));
   std::vector<int> st(nitems);
   CK(cudaMemcpyAsync(st.data(), g.d_status, nitems * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
@@ -597,13 +636,14 @@ int galcamb_evolve_sources_(void) {
   // c[0] = right-hand-side evaluations of the reference algorithm: k1..k8 of every trial step
   // (k1 not after a rejected one) + one per output (camb/equations_galileon.f90:1297).  K1 executes c[5] of them:
   // the y' of an output is the k1 of the next step (c[4] outputs served that way), a rejected step re-forms its k1.
-  g.counters[0] = (double)c[0];
+  // (The lane-per-item form counts the executed evaluations in c[0]; the algorithmic count is c[0] + c[4].)
+  g.counters[0] = batch_form ? (double)(c[0] + c[4]) : (double)c[0];
   g.counters[1] = (double)c[1];
   g.counters[2] = (double)c[2];
-  g.evolve_stats[0] = (double)c[5];
+  g.evolve_stats[0] = batch_form ? (double)c[0] : (double)c[5];
   g.evolve_stats[1] = (double)c[4];
-  g.evolve_stats[2] = (double)c[6];
-  if (getenv("GALCAMB_PHASE_PROFILE")) {  // only meaningful for a -DGC_PROFILE_PHASES build: warp-cycles per phase
+  g.evolve_stats[2] = batch_form ? 0.0 : (double)c[6];
+  if (!batch_form && getenv("GALCAMB_PHASE_PROFILE")) {  // only meaningful for a -DGC_PROFILE_PHASES build: warp-cycles per phase
     const char* nm[9] = {"window", "phaseA", "phaseB", "combine", "scalar", "hier", "output", "final", "advance"};
     double tot = 0;
     for (int i = 0; i < 9; i++) tot += (double)c[8 + i];

@@ -10,6 +10,7 @@
 // and the Runge-Kutta columns of an item live in shared memory, unit stride: element i of a column is col[i-1].
 #pragma once
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 
 #include "galileon_fast.cuh"
@@ -34,17 +35,25 @@ namespace gc {
 
 struct EV {
   double q, k, k2, ik, ik2;  // ik = 1/k, ik2 = 1/k^2 (per-lane constants)
-  int w_ix, r_ix, g_ix, polind, nu_pert_ix, nvar, neq;
-  int lmaxg, lmaxnr, lmaxnu, lmaxgpol, lmaxnu_pert;
-  int nu_ix[GC_MAX_NU], nq[GC_MAX_NU], lmaxnu_tau[GC_MAX_NU];
+  // 16/8-bit layout fields: the record sits in shared memory once per work item (csrc/evolve.cu) or per lane
+  // (csrc/evolve_batch.cu: 256 records per SM)
+  short w_ix, r_ix, g_ix, polind, nu_pert_ix, nvar, neq;
+  short lmaxg, lmaxnr, lmaxnu, lmaxgpol, lmaxnu_pert;
+  short nu_ix[GC_MAX_NU];
+  unsigned char nq[GC_MAX_NU], lmaxnu_tau[GC_MAX_NU];
   bool TightCoupling, high_ktau, no_nu, no_phot, has_nu_rel;
   bool MassiveNuApprox[GC_MAX_NU], nu_nonrel[GC_MAX_NU];
   double G11[GC_MAX_NU], G30[GC_MAX_NU], MassiveNuApproxTime[GC_MAX_NU];
   double TightSwitchoffTime, pig, pigdot, poltruncfac;
 };
 
-// column element accessors (1-based i like the reference)
-#define AT(col, i) (col)[(i)-1]
+// column element accessors (1-based i like the reference).  GC_STRIDE = 1: unit-stride columns (shared memory, the
+// eight-lane kernel csrc/evolve.cu); GC_STRIDE = 32: lane-interleaved columns of the lane-per-item batch kernel
+// (csrc/evolve_batch.cu defines it before including this file)
+#ifndef GC_STRIDE
+#define GC_STRIDE 1
+#endif
+#define AT(col, i) (col)[((i)-1) * GC_STRIDE]
 
 __device__ __forceinline__ double denlk(const EV& e, int l) { return c_denl[l] * e.k * l; }
 __device__ __forceinline__ double denlk2(const EV& e, int l) { return c_denl[l] * e.k * 1.0 * (l + 1); }
@@ -270,7 +279,7 @@ __device__ inline int next_nu_nq(const DevModel& M, int nq) {
 }
 
 // camb/equations_galileon.f90:555-644
-__device__ inline void SetupScalarArrayIndices(const DevModel& M, EV& e, int* max_num_eqns) {
+__device__ inline void SetupScalarArrayIndices(const DevModel& M, EV& e, short* max_num_eqns) {
   int neq = 5, maxeq = 5;
   if (!e.no_phot) {
     e.g_ix = 6;
@@ -333,7 +342,7 @@ __device__ inline void SetupScalarArrayIndices(const DevModel& M, EV& e, int* ma
     e.has_nu_rel = false;
   }
   e.neq = neq;
-  if (max_num_eqns) *max_num_eqns = maxeq;
+  if (max_num_eqns) *max_num_eqns = (short)maxeq;
 }
 
 // camb/equations_galileon.f90:646-724 ; y, yout are workspace columns

@@ -34,19 +34,20 @@ struct GcRegions {
 struct DevModel {
   // ---- hot block: everything derivs() reads, packed into the first ~3 cache lines so that a warp whose 32
   // lanes belong to 32 different models keeps its constants L1 resident (12 warps x 32 models x ~350 B)
-  double grhom, grhog, grhor, grhob, grhoc, grhov, grhornomass, grhok;   // camb/modules.f90:171-193
+  double grhom, grhog, grhob, grhoc, grhov, grhornomass, grhok;   // camb/modules.f90:171-193
   double c2, c3, c4, c5, cG, h0, orad;                                   // camb/galileon.cc:80-92
   double tauminn, dlntau, dlnam;
   double inv_tauminn, inv_dlntau, inv_dlnam;  // reciprocals used by the table-index computations
   double inv_nu_q[GC_MAX_NQ];
   double gal_lnq_inv, gal_a0;  // index guess into the background table: i ~ log(a/a0)*gal_lnq_inv
   double grhormass[GC_MAX_NU], nu_masses[GC_MAX_NU];
-  double nu_q[GC_MAX_NQ], nu_int_kernel[GC_MAX_NQ];
+  double nu_int_kernel[GC_MAX_NQ];
   const double* th;
   const double* gal;
   const double* nu_tab;  // [GC_NRHOPN][6] = {r1, dr1, p1, dp1, ddr1, ddp1} rows (shared by all models)
   int use_galileon, n_eig, Num_Nu_massive, nqmax, nthermo, ngal;
   // ---- everything else
+  double grhor, nu_q[GC_MAX_NQ];
   double adotrad, tau0, taurst, taurend, tau_maxvis, tight_tau, matter_verydom_tau, epsw;
   double max_etak_scalar, AccuracyBoost, lAccuracyBoost, tol1;
   int DoLateRadTruncation, HighAccuracyDefault, AccuratePolarization, AccurateReionization;

@@ -293,20 +293,38 @@ def test_distinct_cosmology_batch(gpu):
 
 
 def test_distinct_cosmology_batch_in_batch_mode():
-    """The same kind of batch through the lock-step launch shape (4-warp CTAs, all columns in global memory), which the
-    launcher only picks above ~800 models: forced here with GALCAMB_LATENCY_ITEMS=0 in a fresh process (the knob is read
-    once per process).  40 distinct points = one full warp and one warp of 8 items (cooperative combine) per k index."""
+    """The same kind of batch through the lane-per-item form of K1 (csrc/evolve_batch.cu) in its lock-step launch shape
+    (4-warp CTAs), which the launcher only picks for large batches: forced here with GALCAMB_OCTET_ITEMS=0 (lane-per-item
+    form whatever the size) and GALCAMB_LATENCY_ITEMS=0 (lock-step CTAs) in a fresh process (the knobs are read once per
+    process).  40 distinct points = one full warp and one warp of 8 items (cooperative combine) per k index."""
     import re
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, GALCAMB_LATENCY_ITEMS="0")
+    env = dict(os.environ, GALCAMB_LATENCY_ITEMS="0", GALCAMB_OCTET_ITEMS="0")
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_hetero_probe.py"), "40"], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert len(re.findall(r"failed slots 0;", r.stdout)) == 2, r.stdout
     m = re.search(r"vs the oracle: ([0-9.e+-]+)", r.stdout)
     assert m and float(m.group(1)) < TOL_CL, r.stdout
+
+
+def test_both_forms_of_k1_on_the_golden_fixture():
+    """The committed config-2 fixture through each form of K1 (eight lanes per item / one lane per item, one-warp CTAs),
+    forced by GALCAMB_OCTET_ITEMS in fresh processes: both reproduce the golden sources and C_l."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for knob in ("1000000000", "0"):
+        env = dict(os.environ, GALCAMB_OCTET_ITEMS=knob)
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_k1_probe.py"), "3"], env=env, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        m = re.search(r"Cl err ([0-9.e+-]+) Src err ([0-9.e+-]+) identical=True", r.stdout)
+        assert m, r.stdout
+        assert float(m.group(1)) < TOL_CL and float(m.group(2)) < TOL_TRANSFER, r.stdout
 
 
 def test_massless_neutrino_model(gpu):
