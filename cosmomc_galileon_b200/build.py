@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 VARIANT = os.environ.get("GALCAMB_VARIANT", "")
 OBJ = os.path.join(HERE, "_build" + ("_" + VARIANT if VARIANT else ""))
 LIB = os.path.join(HERE, "libgalcamb_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
-SOURCES = ["evolve.cu", "evolve_batch.cu", "los.cu", "lensing.cu", "capi.cu", "fp64_peak.cu", "galileon_host.cu"]
+SOURCES = ["evolve.cu", "evolve_batch.cu", "los.cu", "lensing.cu", "capi.cu", "fp64_peak.cu", "galileon_host.cu", "prestage.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FMAD = os.environ.get("GALCAMB_FMAD", "true")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=" + FMAD, "-std=c++17", "-Xcompiler",

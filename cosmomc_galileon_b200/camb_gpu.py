@@ -54,6 +54,54 @@ class CModel(C.Structure):
     )
 
 
+class CParams(C.Structure):
+    """struct galcamb_params of include/galcamb.h (field order must match): the CAMBparams subset of the scalar path."""
+    _fields_ = (
+        [(n, _D) for n in "H0 omegab omegac omegav omegan TCMB YHe Num_Nu_massless".split()]
+        + [(n, _I) for n in "Num_Nu_massive Nu_mass_eigenstates share_delta_neff".split()]
+        + [("Nu_mass_degeneracies", _D * MAX_NU), ("Nu_mass_fractions", _D * MAX_NU), ("Nu_mass_numbers", _I * MAX_NU)]
+        + [("use_galileon", _I)]
+        + [(n, _D) for n in "c2 c3 c4 cG ScalarPowerAmp an n_run n_runrun k_0_scalar".split()]
+        + [("Reionization", _I), ("use_optical_depth", _I)]
+        + [(n, _D) for n in ("optical_depth reion_redshift delta_redshift reion_fraction helium_redshift "
+                             "helium_delta_redshift helium_redshiftstart RECFAST_fudge RECFAST_fudge_He").split()]
+        + [("RECFAST_Heswitch", _I), ("RECFAST_Hswitch", _I), ("Max_l", _I), ("Max_eta_k", _D)]
+        + [(n, _I) for n in ("DoLensing AccuratePolarization AccurateReionization MassiveNuMethod DoLateRadTruncation "
+                             "HighAccuracyDefault").split()]
+        + [(n, _D) for n in "AccuracyBoost lSampleBoost lAccuracyBoost".split()]
+        + [("use_spline_template", _I)]
+    )
+
+
+def make_params(ombh2=None, omch2=None, omnuh2=None, **kw):
+    """CParams from CAMB-style keywords: the defaults of galcamb_default_params_, then physical densities (ombh2, omch2,
+    omnuh2 -> omegab, omegac, omegan with omegav closing the universe, as camb/inidriver.F90:108-121 does) and any
+    field of galcamb_params by name.  Arrays (Nu_mass_*) take sequences."""
+    p = CParams()
+    load_library().galcamb_default_params_(C.byref(p))
+    H0 = kw.get("H0", p.H0)
+    h2 = (H0 / 100.0) ** 2
+    if ombh2 is not None:
+        p.omegab = ombh2 / h2
+    if omch2 is not None:
+        p.omegac = omch2 / h2
+    if omnuh2 is not None:
+        p.omegan = omnuh2 / h2
+    names = {n for n, _ in CParams._fields_}
+    for k, v in kw.items():
+        if k not in names:
+            raise KeyError("galcamb_params has no field %r" % k)
+        if k.startswith("Nu_mass_") and k != "Nu_mass_eigenstates":
+            arr = getattr(p, k)
+            for i, x in enumerate(v):
+                arr[i] = x
+        else:
+            setattr(p, k, v)
+    if "omegav" not in kw:
+        p.omegav = 1.0 - p.omegab - p.omegac - p.omegan
+    return p
+
+
 SCALARS = [n for n, t in CModel._fields_ if t in (_D, _I)]
 ARRAYS = [n for n, t in CModel._fields_ if t is _P]
 SMALL = ["grhormass", "nu_masses", "nu_q", "nu_int_kernel", "nu_tau_notmassless", "nu_tau_nonrelativistic", "nu_tau_massive"]
@@ -171,12 +219,77 @@ def load_library():
         L.galcamb_get_timings_.argtypes = [C.c_void_p]
         L.galcamb_get_counters_.argtypes = [C.c_void_p]
         L.galcamb_get_evolve_stats_.argtypes = [C.c_void_p]
+        L.galcamb_default_params_.argtypes = [C.POINTER(CParams)]
+        L.galcamb_default_params_.restype = None
+        L.galcamb_prestage_.argtypes = [C.POINTER(CParams), C.POINTER(_I), C.POINTER(_I)]
+        L.galcamb_prestage_status_.argtypes = [C.POINTER(_I), C.POINTER(_I)]
+        L.galcamb_prestage_error_.restype = C.c_char_p
+        L.galcamb_prestage_model_.argtypes = [C.POINTER(_I), C.POINTER(CModel)]
+        L.galcamb_prestage_lsamples_.argtypes = [C.POINTER(_I), C.POINTER(_I), C.c_void_p, C.POINTER(_I)]
+        L.galcamb_prestage_free_.restype = None
+        L.galcamb_params_to_cls_.argtypes = [C.POINTER(CParams), C.POINTER(_I), C.POINTER(_I), C.c_void_p]
         _lib = L
     return _lib
 
 
 class GalCambError(RuntimeError):
     pass
+
+
+def prestage(params, nthreads=0, copy=True):
+    """galcamb_prestage_ for a list of CParams: CAMBParams_Set + InitVars + the k grids + l sampling on the host threads
+    (no GPU needed).  Returns (tables, status): tables[i] is a ModelTables (None for a rejected point), status[i] the
+    CAMB error id.  copy=False leaves the arrays as views into the library's buffers (valid until the next call)."""
+    L = load_library()
+    n = len(params)
+    arr = (CParams * n)(*params)
+    L.galcamb_prestage_(arr, C.byref(_I(n)), C.byref(_I(nthreads)))
+    tables, status = [], []
+    for i in range(n):
+        st = _I(0)
+        L.galcamb_prestage_status_(C.byref(_I(i)), C.byref(st))
+        status.append(st.value)
+        if st.value:
+            tables.append(None)
+            continue
+        m = CModel()
+        rc = L.galcamb_prestage_model_(C.byref(_I(i)), C.byref(m))
+        assert rc == 0
+        nl, kmax = _I(0), _I(0)
+        L.galcamb_prestage_lsamples_(C.byref(_I(i)), C.byref(nl), None, C.byref(kmax))
+        ls = np.zeros(nl.value, dtype=np.int32)
+        L.galcamb_prestage_lsamples_(C.byref(_I(i)), C.byref(nl), ls.ctypes.data, C.byref(kmax))
+        d = {}
+        for name in SCALARS:
+            if name != "n_tau_regions":
+                d[name] = getattr(m, name)
+        sizes = dict(nu_r1=2000, nu_p1=2000, nu_dr1=2000, nu_dp1=2000, nu_ddr1=2000, nu_ddp1=2000, cs2=m.nthermo,
+                     dcs2=m.nthermo, dotmu=m.nthermo, ddotmu=m.nthermo, dddotmu=m.nthermo, tau=m.nt, dtau=m.nt, vis=m.nt,
+                     dvis=m.nt, ddvis=m.nt, expmmu=m.nt, opac=m.nt, dopac=m.nt, gal_a=m.ngal, gal_h=m.ngal, gal_x=m.ngal,
+                     k=m.nk, q=m.nq, dq=m.nq)
+        for name in ARRAYS:
+            ptr = getattr(m, name)
+            if not ptr or sizes[name] == 0:
+                d[name] = np.zeros(0)
+            else:
+                a = np.ctypeslib.as_array(ptr, shape=(sizes[name],))
+                d[name] = a.copy() if copy else a
+        ne = m.Nu_mass_eigenstates
+        d["grhormass"] = np.array(m.grhormass[:ne])
+        d["nu_masses"] = np.array(m.nu_masses[:ne])
+        d["nu_tau_nonrelativistic"] = np.array(m.nu_tau_nonrelativistic[:ne])
+        d["nu_tau_massive"] = np.array(m.nu_tau_massive[:ne])
+        nqm = m.nqmax if ne else 0
+        d["nu_q"] = np.array(m.nu_q[:nqm])
+        d["nu_int_kernel"] = np.array(m.nu_int_kernel[:nqm])
+        d["nu_tau_notmassless"] = np.array([[m.nu_tau_notmassless[q][e] for e in range(ne)] for q in range(nqm)]).reshape(nqm, ne)
+        if not ne:
+            d["nqmax"] = 0
+        d["tau_regions"] = np.array([[r.Low, r.High, r.delta, r.start_index, r.IsLog] for r in m.tau_regions[: m.n_tau_regions]])
+        d["ls"] = ls
+        d["kmaxfile"] = kmax.value
+        tables.append(ModelTables(d))
+    return tables, status
 
 
 class GalCamb:

@@ -916,6 +916,40 @@ int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* 
   return rc_ev;
 }
 
+// Parameters -> C_l: the host pre-stage (csrc/prestage.cu, one host thread per point) followed by stages 1-4 on the
+// device.  Points the pre-stage rejects (unstable Galileon background, reionization not converged ...) are left out
+// of the device batch and come back as NaN rows, like points whose integration fails.
+int galcamb_params_to_cls_(const galcamb_params* params, const int* n, const int* nthreads, double* Cl_out) {
+  if (!g.ready) return fail(100, "not initialised");
+  const int rc_pre = galcamb_prestage_(params, n, nthreads);
+  std::vector<galcamb_model> models;
+  std::vector<int> where;
+  for (int i = 0; i < *n; i++) {
+    galcamb_model m;
+    if (galcamb_prestage_model_(&i, &m) == 0) {
+      models.push_back(m);
+      where.push_back(i);
+    }
+  }
+  const size_t per = (size_t)3 * (params[0].Max_l - 1);
+  for (size_t j = 0; j < per * (size_t)*n; j++) Cl_out[j] = std::nan("");
+  if (models.empty()) return rc_pre ? rc_pre : fail(5, "no valid point in the batch");
+  {  // Bessel tables for this l sampling / x range (cached across calls like camb/bessels.f90:40-41)
+    int nl = 0, kmaxfile = 0;
+    galcamb_prestage_lsamples_(&where[0], &nl, nullptr, &kmaxfile);
+    std::vector<int> ls(nl);
+    galcamb_prestage_lsamples_(&where[0], &nl, ls.data(), &kmaxfile);
+    const double boost = params[0].AccuracyBoost;
+    if (int rc = galcamb_set_bessels_(ls.data(), &nl, &kmaxfile, &boost)) return rc;  // returns at once when cached
+  }
+  const int nm = (int)models.size();
+  std::vector<double> out(per * nm);
+  const int rc = galcamb_batch_cls_(models.data(), &nm, out.data());
+  if (rc != 0 && rc != 4) return rc;
+  for (int j = 0; j < nm; j++) std::copy(out.begin() + per * j, out.begin() + per * (j + 1), Cl_out + per * where[j]);
+  return rc ? rc : rc_pre;
+}
+
 // galcamb_batch_cls_ followed by the lensing post-step: what CAMB_GetResults hands CosmoMC when DoLensing = T
 // (Cl_lensed, camb/camb.f90:167-171 -> camb/lensing.f90:78).  Cl_out may be NULL.
 int galcamb_batch_lensed_cls_(const galcamb_model* models, const int* nmodels, double* Cl_out, int* lmax_lensed,

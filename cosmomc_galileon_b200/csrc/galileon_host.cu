@@ -259,6 +259,51 @@ int Background::run(double om, bool reject_negative_density, std::vector<double>
   return 0;
 }
 
+// flatness closure: the highest non-zero coefficient follows from the others (camb/galileon.cc:520-575)
+static void close_coefficients(Background& B, double om, double c3in, double c4in) {
+  DevModel& M = B.M;
+  const int neig = M.n_eig;
+  const double grhom = 3 * (M.h0 * M.h0);
+  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
+  B.nu_pressures(1.0, rhonu, pnu);
+  if (c3in == 0 && c4in == 0) {
+    M.c3 = 0.5 * (-1. + om + M.orad + M.c2 / 6. - 3 * M.cG);
+    for (int i = 0; i < neig; i++) M.c3 += 0.5 * rhonu[i] * M.grhormass[i] / grhom;
+    M.c4 = 0;
+    M.c5 = 0;
+  } else if (c4in == 0) {
+    M.c3 = c3in;
+    // the reference's right-hand side reads the c4 left over from the previous call (:546); kept
+    M.c4 = (1. - om - M.orad - M.c2 / 6. + 2 * M.c3 - 7.5 * M.c4 + 3 * M.cG) / 7.5;
+    for (int i = 0; i < neig; i++) M.c4 += -rhonu[i] * M.grhormass[i] / (7.5 * grhom);
+    M.c5 = 0;
+  } else {
+    M.c3 = c3in;
+    M.c4 = c4in;
+    M.c5 = (-1. + om + M.orad + M.c2 / 6. - 2 * M.c3 + 7.5 * M.c4 - 3 * M.cG) / 7.;
+    for (int i = 0; i < neig; i++) M.c5 += rhonu[i] * M.grhormass[i] / (7. * grhom);
+  }
+}
+
+// ascending-a tables of NB + 2 nodes from the integration grid (descending a), with the linearly extrapolated node
+// beyond a = 1 (camb/galileon.cc:655-663)
+static void ascending_tables(const std::vector<double>& grid, const std::vector<double>& hub, const std::vector<double>& xg,
+                             std::vector<double>& a, std::vector<double>& h, std::vector<double>& x) {
+  const int n = NB + 2;
+  a.assign(n, 0);
+  h.assign(n, 0);
+  x.assign(n, 0);
+  for (int i = 0; i <= NB; i++) {
+    a[i] = grid[NB - i];
+    h[i] = hub[NB - i];
+    x[i] = xg[NB - i];
+  }
+  const double q = std::pow(1e-10 / 1., 1. / NB);
+  a[NB + 1] = 1. / q;
+  h[NB + 1] = (h[NB] - h[NB - 1]) / (a[NB] - a[NB - 1]) * (a[NB + 1] - a[NB - 1]) + h[NB - 1];
+  x[NB + 1] = (x[NB] - x[NB - 1]) / (a[NB] - a[NB - 1]) * (a[NB + 1] - a[NB - 1]) + x[NB - 1];
+}
+
 // exact integral of the natural spline between two abscissae (what gsl_spline_eval_integ returns)
 double spline_integral(const std::vector<double>& xa, const std::vector<double>& ya, const std::vector<double>& c,
                        double a, double b) {
@@ -328,48 +373,49 @@ int arrays_(double* omegar, double* omegam, double* H0in, double* c2in, double* 
   M.h0 = *H0in;
   M.c2 = *c2in;
   M.cG = *cGin;
-  const double grhom = 3 * (M.h0 * M.h0);
-  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
-  nu_pressures(1.0, rhonu, pnu);
-  // flatness closure: the highest non-zero coefficient follows from the others (:520-575)
-  if (*c3in == 0 && *c4in == 0) {
-    M.c3 = 0.5 * (-1. + G.om + M.orad + M.c2 / 6. - 3 * M.cG);
-    for (int i = 0; i < neig; i++) M.c3 += 0.5 * rhonu[i] * M.grhormass[i] / grhom;
-    M.c4 = 0;
-    M.c5 = 0;
-  } else if (*c4in == 0) {
-    M.c3 = *c3in;
-    // the reference's right-hand side reads the c4 left over from the previous call (:546); kept
-    M.c4 = (1. - G.om - M.orad - M.c2 / 6. + 2 * M.c3 - 7.5 * M.c4 + 3 * M.cG) / 7.5;
-    for (int i = 0; i < neig; i++) M.c4 += -rhonu[i] * M.grhormass[i] / (7.5 * grhom);
-    M.c5 = 0;
-  } else {
-    M.c3 = *c3in;
-    M.c4 = *c4in;
-    M.c5 = (-1. + G.om + M.orad + M.c2 / 6. - 2 * M.c3 + 7.5 * M.c4 - 3 * M.cG) / 7.;
-    for (int i = 0; i < neig; i++) M.c5 += rhonu[i] * M.grhormass[i] / (7. * grhom);
-  }
+  close_coefficients(G, G.om, *c3in, *c4in);
   std::vector<double> grid, hub, xg;
   if (int status = G.run(G.om, false, grid, hub, xg)) return status;
-  const int n = NB + 2;
-  G.a.assign(n, 0);
-  G.h.assign(n, 0);
-  G.x.assign(n, 0);
-  for (int i = 0; i <= NB; i++) {
-    G.a[i] = grid[NB - i];
-    G.h[i] = hub[NB - i];
-    G.x[i] = xg[NB - i];
-  }
-  // one linearly extrapolated node beyond a = 1 (:655-663)
-  const double q = std::pow(1e-10 / 1., 1. / NB);
-  G.a[NB + 1] = 1. / q;
-  G.h[NB + 1] = (G.h[NB] - G.h[NB - 1]) / (G.a[NB] - G.a[NB - 1]) * (G.a[NB + 1] - G.a[NB - 1]) + G.h[NB - 1];
-  G.x[NB + 1] = (G.x[NB] - G.x[NB - 1]) / (G.a[NB] - G.a[NB - 1]) * (G.a[NB + 1] - G.a[NB - 1]) + G.x[NB - 1];
+  ascending_tables(grid, hub, xg, G.a, G.h, G.x);
   spline_coefficients(G.a, G.h, G.ch);
   spline_coefficients(G.a, G.x, G.cx);
   G.ready = true;
   return 0;
 }
+
+}  // extern "C"
+
+// Re-entrant form of arrays_ for the batched pre-stage (csrc/prestage.cu): one Background per call, no file-scope
+// state, so host threads integrate different cosmologies side by side.  nu_tab = [n][6] rows {r1, dr1, p1, dp1, ddr1,
+// ddp1}.  coef = {c2, c3, c4, c5, cG} after the flatness closure; a/h/x = NB + 2 ascending nodes.
+int gc_galileon_background(double omegar, double omegam, double h0, double c2, double c3in, double c4in, double cG, int neig,
+                           const double* grhormass, const double* nu_masses, const double* nu_tab, double dlnam, double* coef,
+                           std::vector<double>& a, std::vector<double>& h, std::vector<double>& x) {
+  if (neig < 0 || neig > GC_MAX_NU) return 5;
+  Background B;
+  DevModel& M = B.M;
+  M.n_eig = neig;
+  for (int i = 0; i < neig; i++) {
+    M.grhormass[i] = grhormass[i];
+    M.nu_masses[i] = nu_masses[i];
+  }
+  M.nu_tab = nu_tab;
+  M.dlnam = dlnam;
+  M.inv_dlnam = 1.0 / dlnam;
+  M.orad = omegar;
+  M.h0 = h0;
+  M.c2 = c2;
+  M.cG = cG;
+  M.c3 = M.c4 = M.c5 = 0;
+  close_coefficients(B, omegam, c3in, c4in);
+  std::vector<double> grid, hub, xg;
+  if (int status = B.run(omegam, false, grid, hub, xg)) return status;
+  ascending_tables(grid, hub, xg, a, h, x);
+  coef[0] = M.c2; coef[1] = M.c3; coef[2] = M.c4; coef[3] = M.c5; coef[4] = M.cG;
+  return 0;
+}
+
+extern "C" {
 
 // camb/theta.cc:296-426 -- theta = r_s(a*) / D_A(a*) for the theta <-> H0 solve of CosmoMC
 // (source/CosmologyParameterizations.f90:263-271).  Its own background problem: the tables of arrays_ are untouched.

@@ -143,6 +143,49 @@ int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* 
 int galcamb_batch_lensed_cls_(const galcamb_model* models, const int* nmodels, double* Cl_out, int* lmax_lensed,
                               double* Cl_lensed_out);
 
+/* --- host pre-stage (csrc/prestage.cu) ------------------------------------------------------------------
+ * The subset of CAMBparams (camb/modules.f90:98-167) and of the module-level accuracy knobs (:202-214) the scalar,
+ * flat path reads; same names and meaning as the reference.  galcamb_default_params_ fills the defaults of
+ * camb/inidriver.F90 / CAMB_SetDefParams (camb/camb.f90:214-269). */
+typedef struct galcamb_params {
+  double H0, omegab, omegac, omegav, omegan;     /* CP%H0, CP%omegab ... (fractions of the critical density) */
+  double TCMB, YHe, Num_Nu_massless;
+  int Num_Nu_massive, Nu_mass_eigenstates, share_delta_neff;
+  double Nu_mass_degeneracies[GALCAMB_MAX_NU], Nu_mass_fractions[GALCAMB_MAX_NU];
+  int Nu_mass_numbers[GALCAMB_MAX_NU];
+  int use_galileon;                              /* camb/modules.f90:164-165 */
+  double c2, c3, c4, cG;                         /* c5 / the highest non-zero coefficient follows from flatness */
+  double ScalarPowerAmp, an, n_run, n_runrun, k_0_scalar; /* camb/power_tilt.f90:60-92 */
+  int Reionization, use_optical_depth;           /* camb/reionization.f90:64-77 */
+  double optical_depth, reion_redshift, delta_redshift, reion_fraction;
+  double helium_redshift, helium_delta_redshift, helium_redshiftstart;
+  double RECFAST_fudge, RECFAST_fudge_He;        /* camb/recfast.f90:257-282 (fudge already shifted for Hswitch) */
+  int RECFAST_Heswitch, RECFAST_Hswitch;
+  int Max_l;
+  double Max_eta_k;
+  int DoLensing, AccuratePolarization, AccurateReionization, MassiveNuMethod, DoLateRadTruncation, HighAccuracyDefault;
+  double AccuracyBoost, lSampleBoost, lAccuracyBoost;
+  int use_spline_template;
+} galcamb_params;
+
+void galcamb_default_params_(galcamb_params* p);
+int galcamb_sizeof_params_(void);
+/* CAMBParams_Set (camb/modules.f90:260) + InitVars (camb/cmbmain.f90:722) + SetkValuesForSources (:797) +
+ * SetkValuesForInt (:1281) + initlval (camb/modules.f90:851) for n parameter points, spread over *nthreads host threads
+ * (0 = all cores).  The tables stay in the library until the next call / galcamb_prestage_free_; a point that fails
+ * keeps its CAMB error id (galcamb_prestage_status_) and the call returns the first such id. */
+int galcamb_prestage_(const galcamb_params* params, const int* n, const int* nthreads);
+int galcamb_prestage_status_(const int* i, int* status);
+const char* galcamb_prestage_error_(void);
+/* a galcamb_model whose pointers look into the tables of point i (valid until the next pre-stage call) */
+int galcamb_prestage_model_(const int* i, galcamb_model* m);
+/* lSamp%l(1:l0) and the Bessel x range of point i: the arguments of galcamb_set_bessels_ (ls may be NULL to query nl) */
+int galcamb_prestage_lsamples_(const int* i, int* nl, int* ls, int* kmaxfile);
+void galcamb_prestage_free_(void);
+/* parameters -> C_l in one call: pre-stage on the host threads, stages 1-4 on the device.  Points the pre-stage or the
+ * integration rejects come back as NaN rows; Cl_out as in galcamb_batch_cls_. */
+int galcamb_params_to_cls_(const galcamb_params* params, const int* n, const int* nthreads, double* Cl_out);
+
 /* measurement hooks (bench.py): last stage durations in ms (CUDA events on the library stream) and the
  * algorithmic work counters of SURVEY.md section 8(d). */
 int galcamb_get_timings_(double* ms /*[8]: evolve, spline_k, los, cls, lensing, -, bessel, total of 0..3*/);

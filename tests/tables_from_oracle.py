@@ -26,15 +26,14 @@ def tables_from_oracle(o, params, lmax=2500):
     d["Nu_mass_eigenstates"] = ne
     d["Num_Nu_massive"] = o.geti("Num_Nu_massive")
     if ne > 0:
-        assert ne == 1, "fixture builder handles one eigenstate"
         d["nqmax"] = o.geti("nu_nqmax")
-        d["grhormass"] = [g("grhormass1")]
-        d["nu_masses"] = [g("nu_masses1")]
+        d["grhormass"] = [g("grhormass%d" % (i + 1)) for i in range(ne)]
+        d["nu_masses"] = [g("nu_masses%d" % (i + 1)) for i in range(ne)]
         d["nu_q"] = o.arr("nu_q")
         d["nu_int_kernel"] = o.arr("nu_int_kernel")
-        d["nu_tau_notmassless"] = o.arr("nu_tau_notmassless1").reshape(-1, 1)
-        d["nu_tau_nonrelativistic"] = [g("nu_tau_nonrelativistic1")]
-        d["nu_tau_massive"] = [g("nu_tau_massive1")]
+        d["nu_tau_notmassless"] = np.stack([o.arr("nu_tau_notmassless%d" % (i + 1)) for i in range(ne)], axis=1)  # [iq][eig]
+        d["nu_tau_nonrelativistic"] = [g("nu_tau_nonrelativistic%d" % (i + 1)) for i in range(ne)]
+        d["nu_tau_massive"] = [g("nu_tau_massive%d" % (i + 1)) for i in range(ne)]
         d["dlnam"] = g("nu_dlnam")
         for n in "r1 p1 dr1 dp1 ddr1 ddp1".split():
             d["nu_" + n] = o.arr("nu_" + n)
