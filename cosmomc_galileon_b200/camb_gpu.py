@@ -424,6 +424,17 @@ class GalCamb:
             self._chk(rc)
         return out
 
+    # parameters -> C_l: host pre-stage (CAMBParams_Set ... SetkValuesForInt on the host threads) + stages 1-4 on the device
+    def params_to_cls(self, params, nthreads=0, out=None):
+        n = len(params)
+        arr = (CParams * n)(*params)
+        if out is None:
+            out = np.zeros((n, 3, params[0].Max_l - 1))
+        rc = self.L.galcamb_params_to_cls_(arr, C.byref(_I(n)), C.byref(_I(nthreads)), out.ctypes.data)
+        if rc not in (0, 1, 2, 4, 6):  # per-point rejections (reionization, recombination, evolution, background): NaN rows
+            self._chk(rc)
+        return out
+
     # the same with the lensing post-step: (Cl[n,3,lmax-1], Cl_lensed[n,4,lmax_lensed-1])
     def batch_lensed_cls(self, models):
         n = len(models)

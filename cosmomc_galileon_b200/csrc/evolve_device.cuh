@@ -68,10 +68,14 @@ GC_HOSTDEV __forceinline__ double herm(double f0, double d0, double f1, double d
 
 // camb/modules.f90:2728-2769
 __device__ inline void thermo(const DevModel& M, double tau, double& cs2b, double& opacity, double* dopacity) {
+  const int nth = M.nthermo;
   double d = log(tau * M.inv_tauminn) * M.inv_dlntau + 1.0;
+  // The last node is a branch point (below it the Hermite cubic, from it on the reference's end-of-table formula, which
+  // is NOT its continuation), and tau = tau0 sits exactly on it: there the index has to come out of the reference's own
+  // arithmetic, two divisions instead of the reciprocal multiplies.
+  if (d > nth - 0.5) d = log(tau / M.tauminn) / M.dlntau + 1.0;
   int i = (int)d;
   d = d - i;
-  const int nth = M.nthermo;
   if (i >= nth) {
     const double* r = M.th + (size_t)(nth - 1) * 5;
     cs2b = GC_LDG(r) + (d + i - nth) * GC_LDG(r + 1);

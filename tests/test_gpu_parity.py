@@ -12,6 +12,9 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL_TRANSFER = 1e-6
 TOL_CL = 1e-5
+# per-element bound on the sources: relative for every element above 1e-6 of its source's maximum, absolute (in units of
+# that floor) below; measured 8e-10 on the default (FMA-contracting) build
+TOL_ELEMENT = 1e-6
 GAL = dict(ombh2=0.0221743, omch2=0.1177806, omnuh2=0.00064, H0=78.07227, use_galileon=1, c2=-8.438179, c3=-3.366555,
            c4=-1.03411, cG=0.001188243)
 LCDM = dict(ombh2=0.0226, omch2=0.112, omnuh2=0.00064, H0=70.0)
@@ -19,6 +22,28 @@ LCDM = dict(ombh2=0.0226, omch2=0.112, omnuh2=0.00064, H0=70.0)
 
 def relmax(a, b):
     return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def colmax(S, So):
+    """Sources [t][s][k]: worst max-norm relative error over the (source, k) columns -- every k mode is its own
+    integration with its own amplitude (high-k columns are orders of magnitude below the low-k ones), so this is far
+    stricter than one max-norm over the whole array."""
+    num = np.max(np.abs(S - So), axis=0)
+    den = np.max(np.abs(So), axis=0)
+    ok = den > 0
+    return float(np.max(num[ok] / den[ok])) if np.any(ok) else 0.0
+
+
+def elemmax(S, So, floor=1e-6):
+    """Per-element error: relative where |So| > floor * max|So| of its source, absolute (in units of that floor)
+    elsewhere."""
+    worst = 0.0
+    for s in range(So.shape[1]):
+        m = np.max(np.abs(So[:, s]))
+        if m == 0:
+            continue
+        worst = max(worst, float(np.max(np.abs(S[:, s] - So[:, s]) / np.maximum(np.abs(So[:, s]), floor * m))))
+    return worst
 
 
 @pytest.fixture(scope="module")
@@ -49,6 +74,9 @@ def test_full_path_against_oracle(gpu, P):
     S, So = gpu.Src(), o.Src()
     for s in range(S.shape[1]):
         assert relmax(S[:, s], So[:, s]) < TOL_TRANSFER
+    # per (source, k) column, and per element (relative down to 1e-6 of the source's maximum, absolute below)
+    assert colmax(S, So) < TOL_TRANSFER
+    assert elemmax(S, So) < TOL_ELEMENT, elemmax(S, So)
     assert relmax(gpu.Delta_p_l_k(), o.Delta()) < TOL_TRANSFER
     icl, cl = gpu.Cls()
     assert np.max(np.abs(cl / o.Cl() - 1)) < TOL_CL
@@ -325,6 +353,97 @@ def test_both_forms_of_k1_on_the_golden_fixture():
         m = re.search(r"Cl err ([0-9.e+-]+) Src err ([0-9.e+-]+) identical=True", r.stdout)
         assert m, r.stdout
         assert float(m.group(1)) < TOL_CL and float(m.group(2)) < TOL_TRANSFER, r.stdout
+
+
+NU3 = dict(Nu_mass_eigenstates=3, Num_Nu_massive=3, Num_Nu_massless=0.046)
+FR3 = [0.2, 0.3, 0.5]
+
+
+def oracle_three_eigenstates(P, lmax, **kw):
+    from oracle_py import Oracle
+    o = Oracle(lmax=lmax, **P, **NU3, **kw)
+    for i in range(3):
+        o.set(**{"Nu_mass_numbers%d" % (i + 1): 1, "Nu_mass_fractions%d" % (i + 1): FR3[i]})
+    return o
+
+
+@pytest.mark.parametrize("P,lmax", [(dict(LCDM, omnuh2=0.0015), 1200), (GAL, 1000)], ids=["lcdm", "galileon"])
+def test_three_mass_eigenstates_against_oracle(gpu, P, lmax):
+    """Three massive eigenstates with different masses (camb/inidriver.F90:143-165, the hierarchies CosmoMC sets through
+    CAMB_SetNeutrinoHierarchy, source/Calculator_CAMB.f90:139): three momentum-node blocks in the state vector, three
+    sets of switch times, the per-eigenstate fluid approximation."""
+    from tables_from_oracle import tables_from_oracle
+    o = oracle_three_eigenstates(P, lmax)
+    o.run()
+    assert o.geti("Nu_mass_eigenstates") == 3
+    t = tables_from_oracle(o, dict(P, **NU3), lmax=lmax)
+    assert len(t.d["nu_masses"]) == 3 and len(set(np.round(t.d["nu_masses"], 6))) == 3
+    run_gpu(gpu, t)
+    S, So = gpu.Src(), o.Src()
+    assert colmax(S, So) < TOL_TRANSFER
+    assert relmax(gpu.Delta_p_l_k(), o.Delta()) < TOL_TRANSFER
+    _, cl = gpu.Cls()
+    assert np.max(np.abs(cl / o.Cl() - 1)) < TOL_CL
+    assert abs(gpu.counters()["n_derivs"] / o.get("n_derivs") - 1) < 1e-4
+
+
+def test_three_eigenstates_through_the_batch_kernel():
+    """The same through the lane-per-item form of K1 (forced with GALCAMB_OCTET_ITEMS=0 in a fresh process)."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GALCAMB_OCTET_ITEMS="0")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_nu3_probe.py"), "800"], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    m = re.search(r"colmax ([0-9.e+-]+) cl ([0-9.e+-]+) n_derivs gpu ([0-9]+) oracle ([0-9]+)", r.stdout)
+    assert m and float(m.group(1)) < TOL_TRANSFER and float(m.group(2)) < TOL_CL, r.stdout
+    assert abs(float(m.group(3)) / float(m.group(4)) - 1) < 1e-4
+
+
+def test_parameters_to_cls_without_the_oracle_in_the_loop(gpu):
+    """galcamb_params_to_cls_: parameters in, C_l out, every table built by the product's own pre-stage
+    (csrc/prestage.cu).  Compared with the oracle's C_l for the same parameters; the unstable point comes back as NaN."""
+    from oracle_py import Oracle
+    from cosmomc_galileon_b200 import make_params
+    lmax = 1500
+    pts = [GAL, LCDM, dict(GAL, c2=+5.0), dict(GAL, ombh2=0.0225, omch2=0.1160)]
+    params = [make_params(Max_l=lmax, Max_eta_k=2.0 * lmax, **P) for P in pts]
+    out = gpu.params_to_cls(params)
+    assert np.all(np.isnan(out[2]))
+    for i in (0, 1, 3):
+        o = Oracle(lmax=lmax, **pts[i])
+        o.run()
+        assert np.max(np.abs(out[i] / o.Cl() - 1)) < TOL_CL, i
+
+
+def test_exact_step_history_without_fma_contraction():
+    """Built with -fmad=false (GALCAMB_FMAD=false, own object directory) both forms of K1 take exactly the accept/reject
+    decisions of the CPU oracle (built -ffp-contract=off): the number of right-hand-side evaluations of the reference
+    algorithm is EQUAL, not just close.  The variant library is built on the box if nvcc is there; skipped otherwise."""
+    import re
+    import shutil
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "cosmomc_galileon_b200", "libgalcamb_b200_nofma.so")
+    if not os.path.exists(lib):
+        if not (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+            pytest.skip("no nvcc to build the -fmad=false variant")
+        env = dict(os.environ, GALCAMB_FMAD="false", GALCAMB_VARIANT="nofma")
+        subprocess.check_call([sys.executable, os.path.join(root, "cosmomc_galileon_b200", "build.py")], env=env)
+    gold = np.load(os.path.join(GOLD, "config2_tables.npz"))
+    meta = json.loads(bytes(gold["meta_json"]).decode()) if "meta_json" in gold.files else {}
+    n_oracle = float(meta.get("n_derivs", 6360445.0))
+    for knob in ("1000000000", "0"):
+        env = dict(os.environ, GALCAMB_LIB=lib, GALCAMB_OCTET_ITEMS=knob)
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_k1_probe.py"), "2"], env=env, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        m = re.search(r"'n_derivs': np.float64\(([0-9.]+)\)", r.stdout)
+        assert m, r.stdout
+        assert float(m.group(1)) == 2 * n_oracle, (knob, r.stdout)
 
 
 def test_massless_neutrino_model(gpu):
