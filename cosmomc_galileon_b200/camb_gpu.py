@@ -228,6 +228,11 @@ def load_library():
         L.galcamb_prestage_lsamples_.argtypes = [C.POINTER(_I), C.POINTER(_I), C.c_void_p, C.POINTER(_I)]
         L.galcamb_prestage_free_.restype = None
         L.galcamb_params_to_cls_.argtypes = [C.POINTER(CParams), C.POINTER(_I), C.POINTER(_I), C.c_void_p]
+        L.galcamb_prestage_async_.argtypes = [C.POINTER(CParams), C.POINTER(_I), C.POINTER(_I)]
+        L.galcamb_prestaged_to_cls_.argtypes = [C.c_void_p]
+        L.galcamb_prestaged_upload_.argtypes = []
+        L.galcamb_set_host_threads_.argtypes = [C.POINTER(_I)]
+        L.galcamb_set_host_threads_.restype = None
         _lib = L
     return _lib
 
@@ -434,6 +439,28 @@ class GalCamb:
         if rc not in (0, 1, 2, 4, 6):  # per-point rejections (reionization, recombination, evolution, background): NaN rows
             self._chk(rc)
         return out
+
+    # pipelined form: prestage_async(next batch) overlaps with prestaged_to_cls(current batch)
+    def prestage_async(self, params, nthreads=0):
+        n = len(params)
+        arr = (CParams * n)(*params)
+        self._chk(self.L.galcamb_prestage_async_(arr, C.byref(_I(n)), C.byref(_I(nthreads))))
+
+    def prestage_wait(self):
+        return self.L.galcamb_prestage_wait_()  # first per-point rejection id, 0 if none
+
+    def prestaged_to_cls(self, out):
+        rc = self.L.galcamb_prestaged_to_cls_(out.ctypes.data)
+        if rc not in (0, 4):
+            self._chk(rc)
+        return out
+
+    def prestaged_upload(self):
+        """Tables of the current pre-staged batch -> device (every point must be valid); then the stage methods apply."""
+        self._chk(self.L.galcamb_prestaged_upload_())
+
+    def set_host_threads(self, n):
+        self.L.galcamb_set_host_threads_(C.byref(_I(int(n))))
 
     # the same with the lensing post-step: (Cl[n,3,lmax-1], Cl_lensed[n,4,lmax_lensed-1])
     def batch_lensed_cls(self, models):

@@ -516,6 +516,9 @@ static int upload_models() {
   return 0;
 }
 
+// wavenumber kk of a slot's source grid, from its packed host copy (th | pmin | ts | gal | k | q | dq)
+static double slot_k(const Slot& s, int kk) { return s.staging ? s.staging[s.n_th + s.n_pm + s.n_ts + s.n_gal + kk] : 0.0; }
+
 int galcamb_evolve_sources_(void) {
   if (!g.ready) return fail(100, "not initialised");
   CK(cudaSetDevice(g.device));
@@ -566,14 +569,26 @@ int galcamb_evolve_sources_(void) {
   g.k1_form = batch_form ? 1 : 0;
   g.items.clear();
   int ipw = 4;
+  static int sort_items = -1;
+  if (sort_items < 0) {
+    const char* e = getenv("GALCAMB_SORT_ITEMS");  // experiment knob: 0 = models in slot order within a k index
+    sort_items = e ? atoi(e) : 1;
+  }
   if (batch_form) {
     // every k index starts on a warp boundary (padding items have model = -1): a warp never mixes different k, whose
     // step sequences and switch times differ -- mixing them costs 2-4x.  Low k first: those modes are integrated all the
     // way to tau0 (~7600 trial steps) while k*tau > max_etak_scalar stops the high-k modes at ~800
     // (camb/cmbmain.f90:1034), so the longest items start first and the short ones back-fill the SMs.
+    // Within one k index the lanes of a warp should take similar adaptive step sequences: the models are dealt to the
+    // warps in order of their wavenumber at this index (the k grids of different cosmologies differ by a few per cent
+    // through taurst and tau0), so neighbours in k -- whose oscillation phases and switch times are closest -- share a warp.
+    std::vector<std::pair<double, int>> order;
     for (int kk = 0; kk < max_nk; kk++) {
+      order.clear();
       for (int m = 0; m < nm; m++)
-        if (kk < g.slots[m].host.nk) g.items.push_back(make_int2(m, kk));
+        if (kk < g.slots[m].host.nk) order.emplace_back(sort_items ? slot_k(g.slots[m], kk) : 0.0, m);
+      if (sort_items) std::stable_sort(order.begin(), order.end());
+      for (auto& om : order) g.items.push_back(make_int2(om.second, kk));
       while (g.items.size() % 32) g.items.push_back(make_int2(-1, -1));
     }
   } else {
@@ -585,10 +600,15 @@ int galcamb_evolve_sources_(void) {
     ipw = (int)((total_items + slots_hw - 1) / slots_hw);
     ipw = std::max(1, std::min(ipw, 4));
     if (const char* e = getenv("GALCAMB_ITEMS_PER_WARP")) ipw = std::max(1, std::min(atoi(e), 4));  // experiment knob
+    std::vector<std::pair<double, int>> order;
     for (int kk = 0; kk < max_nk; kk++) {
       int in_group = 0;
-      for (int m = 0; m < nm; m++) {
-        if (kk >= g.slots[m].host.nk) continue;
+      order.clear();
+      for (int m = 0; m < nm; m++)
+        if (kk < g.slots[m].host.nk) order.emplace_back(sort_items ? slot_k(g.slots[m], kk) : 0.0, m);
+      if (sort_items) std::stable_sort(order.begin(), order.end());
+      for (auto& om : order) {
+        const int m = om.second;
         g.items.push_back(make_int2(m, kk));
         if (++in_group == ipw) {
           for (; in_group < 4; in_group++) g.items.push_back(make_int2(-1, -1));
@@ -873,32 +893,56 @@ int galcamb_get_status_(const int* slot, int* status) {
   return 0;
 }
 
-int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* Cl_out) {
+// models -> device slots: AoS packing (+ background spline) on the host threads, then one upload per slot
+int galcamb_batch_upload_(const galcamb_model* models, const int* nmodels) {
   if (!g.ready) return fail(100, "not initialised");
   int rc = galcamb_batch_begin_(nmodels);
   if (rc) return rc;
   CK(cudaSetDevice(g.device));
-  {  // pack the AoS tables (+ background spline) of all models on the host cores, then upload slot by slot
-    const int n = *nmodels;
-    const int nth = std::max(1, std::min<int>(n, (int)std::thread::hardware_concurrency()));
-    std::vector<int> rcs(nth, 0);
-    std::vector<std::thread> pool;
-    std::atomic<int> next(0);
-    for (int t = 0; t < nth; t++)
-      pool.emplace_back([&, t]() {
-        cudaSetDevice(g.device);  // pinned-buffer growth inside pack_model
-        for (;;) {
-          const int i = next.fetch_add(1);
-          if (i >= n) break;
-          if (int r = pack_model(i, &models[i])) rcs[t] = r;
-        }
-      });
-    for (auto& th : pool) th.join();
-    for (int r : rcs)
-      if (r) return r;
-    for (int i = 0; i < n; i++)
-      if ((rc = upload_model(i, &models[i]))) return rc;
-  }
+  const int n = *nmodels;
+  const int hostt = galcamb_get_host_threads_();
+  const int nth = std::max(1, std::min<int>(n, hostt > 0 ? hostt : (int)std::thread::hardware_concurrency()));
+  std::vector<int> rcs(nth, 0);
+  std::vector<std::string> errs(nth);
+  std::vector<std::thread> pool;
+  std::atomic<int> next(0);
+  for (int t = 0; t < nth; t++)
+    pool.emplace_back([&, t]() {
+      cudaSetDevice(g.device);  // pinned-buffer growth inside pack_model
+      for (;;) {
+        const int i = next.fetch_add(1);
+        if (i >= n) break;
+        if (int r = pack_model(i, &models[i])) rcs[t] = r;
+      }
+    });
+  for (auto& th : pool) th.join();
+  for (int r : rcs)
+    if (r) return r;
+  for (int i = 0; i < n; i++)
+    if ((rc = upload_model(i, &models[i]))) return rc;
+  return 0;
+}
+
+// the current pre-staged batch (csrc/prestage.cu) -> device slots; every point must be valid
+int galcamb_prestaged_upload_(void) {
+  const int n = galcamb_prestage_count_();
+  if (n < 1) return fail(5, "no pre-staged batch");
+  std::vector<galcamb_model> models(n);
+  for (int i = 0; i < n; i++)
+    if (galcamb_prestage_model_(&i, &models[i])) return fail(5, "a point of the pre-staged batch was rejected");
+  int nl = 0, kmaxfile = 0, zero = 0;
+  galcamb_prestage_lsamples_(&zero, &nl, nullptr, &kmaxfile);
+  std::vector<int> ls(nl);
+  galcamb_prestage_lsamples_(&zero, &nl, ls.data(), &kmaxfile);
+  const double boost = models[0].AccuracyBoost;
+  if (int rc = galcamb_set_bessels_(ls.data(), &nl, &kmaxfile, &boost)) return rc;
+  return galcamb_batch_upload_(models.data(), &n);
+}
+
+int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* Cl_out) {
+  if (!g.ready) return fail(100, "not initialised");
+  int rc = galcamb_batch_upload_(models, nmodels);
+  if (rc) return rc;
   // A parameter point whose integration fails (CAMB error_evolution) must not sink the batch: its slot keeps the
   // error id (galcamb_get_status_), its C_l come back as NaN, the other points are unaffected (CosmoMC rejects
   // such points one by one, source/Calculator_CAMB.f90:235-243).
@@ -919,34 +963,43 @@ int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* 
 // Parameters -> C_l: the host pre-stage (csrc/prestage.cu, one host thread per point) followed by stages 1-4 on the
 // device.  Points the pre-stage rejects (unstable Galileon background, reionization not converged ...) are left out
 // of the device batch and come back as NaN rows, like points whose integration fails.
-int galcamb_params_to_cls_(const galcamb_params* params, const int* n, const int* nthreads, double* Cl_out) {
+int galcamb_prestaged_to_cls_(double* Cl_out) {
   if (!g.ready) return fail(100, "not initialised");
-  const int rc_pre = galcamb_prestage_(params, n, nthreads);
+  const int n = galcamb_prestage_count_();
+  if (n < 1) return fail(5, "no pre-staged batch");
   std::vector<galcamb_model> models;
   std::vector<int> where;
-  for (int i = 0; i < *n; i++) {
+  for (int i = 0; i < n; i++) {
     galcamb_model m;
     if (galcamb_prestage_model_(&i, &m) == 0) {
       models.push_back(m);
       where.push_back(i);
     }
   }
-  const size_t per = (size_t)3 * (params[0].Max_l - 1);
-  for (size_t j = 0; j < per * (size_t)*n; j++) Cl_out[j] = std::nan("");
-  if (models.empty()) return rc_pre ? rc_pre : fail(5, "no valid point in the batch");
+  if (models.empty()) return fail(5, "no valid point in the batch");
+  const size_t per = (size_t)3 * (models[0].lmax - 1);
+  for (size_t j = 0; j < per * (size_t)n; j++) Cl_out[j] = std::nan("");
   {  // Bessel tables for this l sampling / x range (cached across calls like camb/bessels.f90:40-41)
     int nl = 0, kmaxfile = 0;
     galcamb_prestage_lsamples_(&where[0], &nl, nullptr, &kmaxfile);
     std::vector<int> ls(nl);
     galcamb_prestage_lsamples_(&where[0], &nl, ls.data(), &kmaxfile);
-    const double boost = params[0].AccuracyBoost;
+    const double boost = models[0].AccuracyBoost;
     if (int rc = galcamb_set_bessels_(ls.data(), &nl, &kmaxfile, &boost)) return rc;  // returns at once when cached
   }
   const int nm = (int)models.size();
+  if (nm == n) return galcamb_batch_cls_(models.data(), &nm, Cl_out);
   std::vector<double> out(per * nm);
   const int rc = galcamb_batch_cls_(models.data(), &nm, out.data());
   if (rc != 0 && rc != 4) return rc;
   for (int j = 0; j < nm; j++) std::copy(out.begin() + per * j, out.begin() + per * (j + 1), Cl_out + per * where[j]);
+  return rc;
+}
+
+int galcamb_params_to_cls_(const galcamb_params* params, const int* n, const int* nthreads, double* Cl_out) {
+  if (!g.ready) return fail(100, "not initialised");
+  const int rc_pre = galcamb_prestage_(params, n, nthreads);
+  const int rc = galcamb_prestaged_to_cls_(Cl_out);
   return rc ? rc : rc_pre;
 }
 

@@ -15,7 +15,9 @@
 #pragma once
 #include <cstddef>
 
+#ifndef GC_MAX_NU
 #define GC_MAX_NU 5      // = the reference's max_nu (camb/modules.f90:63)
+#endif
 #define GC_MAX_NQ 5      // momentum nodes (nqmax <= 5 for AccuracyBoost <= 3; camb/modules.f90:1624-1627)
 #define GC_NRHOPN 2000   // camb/modules.f90:1554
 #define GC_MAX_REGIONS 16

@@ -1235,6 +1235,13 @@ int Model::run() {
 // the batch held by the library between galcamb_prestage_ and the next call
 static std::vector<Model> g_batch;
 static std::string g_err;
+// second buffer + worker of the pipelined form (galcamb_prestage_async_ / _wait_)
+static std::vector<Model> g_next;
+static std::string g_next_err;
+static std::vector<galcamb_params> g_async_params;
+static std::thread g_async;
+static int g_async_rc = 0;
+static int g_host_threads = 0;
 
 static void fill_view(const Model& M, galcamb_model* m) {
   std::memset(m, 0, sizeof(*m));
@@ -1306,24 +1313,25 @@ void galcamb_default_params_(galcamb_params* p) {
 
 int galcamb_sizeof_params_(void) { return (int)sizeof(galcamb_params); }
 
-int galcamb_prestage_(const galcamb_params* params, const int* n, const int* nthreads) {
+// the work of galcamb_prestage_ on a given buffer
+static int prestage_into(std::vector<pre::Model>& batch, std::string& err, const galcamb_params* params, int n, int nthreads) {
   using namespace pre;
-  if (*n < 1) {
-    g_err = "n < 1";
-    return 5;
-  }
-  g_batch.clear();
-  g_batch.resize(*n);
-  for (int i = 0; i < *n; i++) g_batch[i].P = params[i];
-  int nt = *nthreads > 0 ? *nthreads : (int)std::thread::hardware_concurrency();
-  nt = std::max(1, std::min(nt, *n));
+  batch.clear();
+  batch.resize(n);
+  for (int i = 0; i < n; i++) batch[i].P = params[i];
+  int nt = nthreads > 0 ? nthreads : g_host_threads > 0 ? g_host_threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min(nt, n));
   // the shared neutrino tables are built by whichever thread gets there first (std::call_once)
   std::atomic<int> next{0};
   auto work = [&]() {
     for (;;) {
       const int i = next.fetch_add(1);
-      if (i >= *n) break;
-      g_batch[i].run();
+      if (i >= n) break;
+      batch[i].run();
+      batch[i].zrec = std::vector<double>();  // the recombination history is only needed up to inithermo
+      batch[i].xrec = std::vector<double>();
+      batch[i].dxrec = std::vector<double>();
+      batch[i].gal_ch = std::vector<double>();
     }
   };
   std::vector<std::thread> th;
@@ -1331,13 +1339,53 @@ int galcamb_prestage_(const galcamb_params* params, const int* n, const int* nth
   work();
   for (auto& t : th) t.join();
   int rc = 0;
-  for (int i = 0; i < *n; i++)
-    if (g_batch[i].status && !rc) {
-      rc = g_batch[i].status;
-      g_err = "point " + std::to_string(i) + ": " + g_batch[i].err;
+  for (int i = 0; i < n; i++)
+    if (batch[i].status && !rc) {
+      rc = batch[i].status;
+      err = "point " + std::to_string(i) + ": " + batch[i].err;
     }
   return rc;
 }
+
+int galcamb_prestage_(const galcamb_params* params, const int* n, const int* nthreads) {
+  if (*n < 1) {
+    pre::g_err = "n < 1";
+    return 5;
+  }
+  return prestage_into(pre::g_batch, pre::g_err, params, *n, *nthreads);
+}
+
+// Pipelined form: galcamb_prestage_async_ starts the same work on a second buffer and returns at once -- the device
+// stages of the CURRENT batch (galcamb_prestaged_to_cls_) run meanwhile; galcamb_prestage_wait_ joins it and makes the
+// new batch the current one.  The parameter array is copied, the caller may reuse it.
+int galcamb_prestage_async_(const galcamb_params* params, const int* n, const int* nthreads) {
+  using namespace pre;
+  if (*n < 1) return 5;
+  if (g_async.joinable()) return 5;  // one batch in flight at a time
+  g_async_params.assign(params, params + *n);
+  const int nth = *nthreads;
+  g_async = std::thread([nth]() {
+    g_async_rc = prestage_into(g_next, g_next_err, g_async_params.data(), (int)g_async_params.size(), nth);
+  });
+  return 0;
+}
+
+int galcamb_prestage_wait_(void) {
+  using namespace pre;
+  if (!g_async.joinable()) return 5;
+  g_async.join();
+  g_batch.swap(g_next);
+  g_next.clear();
+  g_err = g_next_err;
+  return g_async_rc;
+}
+
+int galcamb_prestage_count_(void) { return (int)pre::g_batch.size(); }
+
+// host threads the library may use for the pre-stage and for packing model tables (0 = all cores): with one process per
+// GPU on a shared host each rank passes cores / ranks
+void galcamb_set_host_threads_(const int* n) { pre::g_host_threads = *n; }
+int galcamb_get_host_threads_(void) { return pre::g_host_threads; }
 
 int galcamb_prestage_status_(const int* i, int* status) {
   if (*i < 0 || *i >= (int)pre::g_batch.size()) return 5;

@@ -19,6 +19,31 @@ def shard_models(models, rank, world):
     return models[lo:hi]
 
 
+def gather_cls_to_root(local_cls, n_total, device=None, root=0):
+    """Gather of the per-rank C_l blocks on ONE rank (the one that feeds the likelihoods): (n_total, 3, nL) in the
+    original point order on `root`, None elsewhere.  The blocks travel device to device (NCCL over NVLink when `device`
+    is a GPU); only the root copies the assembled batch back to the host."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    nmax = max(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world))
+    shape = (nmax,) + tuple(local_cls.shape[1:])
+    pad = np.zeros(shape, dtype=np.float64)
+    pad[: local_cls.shape[0]] = local_cls
+    mine = torch.from_numpy(pad)
+    if device is not None:
+        mine = mine.to(device)
+    bufs = [torch.empty(shape, dtype=torch.float64, device=mine.device) for _ in range(world)] if rank == root else None
+    dist.gather(mine, bufs, dst=root)
+    if rank != root:
+        return None
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        parts.append(bufs[r][: hi - lo].cpu().numpy())
+    return np.concatenate(parts, axis=0)
+
+
 def gather_cls(local_cls, n_total, device=None):
     """All-gather of per-rank C_l blocks -> (n_total, 3, nL) on every rank, in the original point order."""
     import torch

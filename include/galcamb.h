@@ -136,6 +136,8 @@ int galcamb_set_primordial_(const int* slot, const double* ScalarPowerAmp, const
 int galcamb_transfers_to_powers_(const int* do_lensing);
 int galcamb_get_lensed_cls_(const int* slot, int* lmax_lensed, double* Cl_lensed /* may be NULL */);
 
+/* batch_begin + set_model for n models at once (tables packed on the host threads) */
+int galcamb_batch_upload_(const galcamb_model* models, const int* nmodels);
 /* one call for a whole batch: set models, run stages 1-4, return Cl(lmin:lmax,3) per model contiguous */
 int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* Cl_out);
 /* the same followed by stage 5: additionally returns Cl_lensed(lmin:lmax_lensed,4) per model contiguous (the caller
@@ -182,6 +184,17 @@ int galcamb_prestage_model_(const int* i, galcamb_model* m);
 /* lSamp%l(1:l0) and the Bessel x range of point i: the arguments of galcamb_set_bessels_ (ls may be NULL to query nl) */
 int galcamb_prestage_lsamples_(const int* i, int* nl, int* ls, int* kmaxfile);
 void galcamb_prestage_free_(void);
+/* pipelined form: _async_ starts the pre-stage of the NEXT batch on a second buffer and returns at once, _wait_ joins it
+ * and makes that batch the current one; galcamb_prestaged_to_cls_ runs stages 1-4 on the current batch (Cl_out as in
+ * galcamb_params_to_cls_, one row per point of the batch, NaN rows for rejected points). */
+int galcamb_prestage_async_(const galcamb_params* params, const int* n, const int* nthreads);
+int galcamb_prestage_wait_(void);
+int galcamb_prestage_count_(void);
+int galcamb_prestaged_to_cls_(double* Cl_out);
+int galcamb_prestaged_upload_(void); /* current pre-staged batch -> device slots (then the stage calls apply) */
+/* host threads the library may use (pre-stage, table packing); 0 = all cores.  One process per GPU: cores / ranks. */
+void galcamb_set_host_threads_(const int* n);
+int galcamb_get_host_threads_(void);
 /* parameters -> C_l in one call: pre-stage on the host threads, stages 1-4 on the device.  Points the pre-stage or the
  * integration rejects come back as NaN rows; Cl_out as in galcamb_batch_cls_. */
 int galcamb_params_to_cls_(const galcamb_params* params, const int* n, const int* nthreads, double* Cl_out);

@@ -10,11 +10,36 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "oracle", "_build", "liborc.so")
+NATIVE_LIB = os.path.join(ROOT, "oracle", "_build", "native", "liborc.so")
 TEMPLATE_F64 = os.path.join(ROOT, "tests", "golden", "highL_template.f64")
 
 
 def build():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "-j8"])
+
+
+def use_native_build():
+    """bench.py's CPU-baseline legs: switch this process to the -O3 -march=native build of the oracle (BASELINE.md
+    section 2), compiled on this machine; returns False (and keeps the strict build) if that build fails or if the
+    library was already loaded."""
+    global LIB
+    if _lib is not None:
+        return LIB == NATIVE_LIB
+    try:
+        # -march=native objects are only valid on the CPU model that built them (the tree travels between machines)
+        cpu = ""
+        try:
+            cpu = next(ln for ln in open("/proc/cpuinfo") if ln.startswith("model name")).strip()
+        except Exception:  # noqa: BLE001
+            pass
+        stamp = os.path.join(os.path.dirname(NATIVE_LIB), ".cpu")
+        same = os.path.exists(stamp) and open(stamp).read() == cpu
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "-j8", "native"] + ([] if same else ["-B"]))
+        open(stamp, "w").write(cpu)
+    except Exception:  # noqa: BLE001
+        return False
+    LIB = NATIVE_LIB
+    return True
 
 
 _lib = None
@@ -86,6 +111,12 @@ class Oracle:
                 raise RuntimeError("template fixture missing: " + TEMPLATE_F64)
         else:
             self.set(use_spline_template=0)
+
+    def set_point(self, **kw):
+        """New parameter point on an existing model object (keeps its cached Bessel tables, camb/bessels.f90:40-41)."""
+        p = dict(kw)
+        self.L.orc_set_physical(self.h, p.pop("ombh2"), p.pop("omch2"), p.pop("omnuh2"), p.pop("H0"))
+        self.set(**p)
 
     def set(self, **kw):
         for k, v in kw.items():

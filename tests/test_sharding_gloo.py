@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from cosmomc_galileon_b200.sharding import gather_cls, shard_range
+from cosmomc_galileon_b200.sharding import gather_cls, gather_cls_to_root, shard_range
 
 
 def test_shard_range_partitions():
@@ -28,6 +28,10 @@ def _worker(rank, world, port, n_total, q):
     # stand-in for the GPU stage: a deterministic "spectrum" per global point index
     local = np.stack([np.full((3, 5), float(i)) + np.arange(5) for i in range(lo, hi)]) if hi > lo else np.zeros((0, 3, 5))
     full = gather_cls(local, n_total)
+    at_root = gather_cls_to_root(local, n_total)
+    assert (at_root is None) == (rank != 0)
+    if rank == 0:
+        np.testing.assert_array_equal(at_root, full)
     q.put((rank, full))
     dist.destroy_process_group()
 
