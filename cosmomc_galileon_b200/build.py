@@ -55,7 +55,7 @@ def build(verbose=False, force=False):
             sys.stderr.write(l)
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, "-ccbin", "/usr/bin/g++"] + objs + ["-lcudart"])
+        subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, "-ccbin", "/usr/bin/g++"] + objs + ["-lcudart", "-ldl"])
     return LIB
 
 

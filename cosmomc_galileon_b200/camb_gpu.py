@@ -233,6 +233,9 @@ def load_library():
         L.galcamb_prestaged_upload_.argtypes = []
         L.galcamb_set_host_threads_.argtypes = [C.POINTER(_I)]
         L.galcamb_set_host_threads_.restype = None
+        L.galcamb_select_device_.argtypes = [C.POINTER(_I)]
+        L.galcamb_multi_params_to_cls_.argtypes = [C.POINTER(_I), C.POINTER(CParams), C.POINTER(_I), C.POINTER(_I), C.c_void_p]
+        L.galcamb_multi_single_cls_.argtypes = [C.POINTER(_I), C.POINTER(CParams), C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -458,6 +461,29 @@ class GalCamb:
     def prestaged_upload(self):
         """Tables of the current pre-staged batch -> device (every point must be valid); then the stage methods apply."""
         self._chk(self.L.galcamb_prestaged_upload_())
+
+    # several GPUs from this one process (include/galcamb.h "several GPUs from one process")
+    def device_count(self):
+        return self.L.galcamb_device_count_()
+
+    def multi_params_to_cls(self, ngpu, params, nthreads=0, out=None):
+        """Parameter-batch sharding over ngpu devices of this box: contiguous blocks of the valid points per device."""
+        n = len(params)
+        arr = (CParams * n)(*params)
+        if out is None:
+            out = np.zeros((n, 3, params[0].Max_l - 1))
+        rc = self.L.galcamb_multi_params_to_cls_(C.byref(_I(ngpu)), arr, C.byref(_I(n)), C.byref(_I(nthreads)), out.ctypes.data)
+        if rc not in (0, 1, 2, 4, 6):
+            self._chk(rc)
+        return out
+
+    def multi_single_cls(self, ngpu, params):
+        """One spectrum over ngpu devices (k-modes dealt round-robin, Src and iCl all-reduced with NCCL).  Returns
+        (Cl[3, lmax-1], dict of milliseconds)."""
+        out = np.zeros((3, params.Max_l - 1))
+        ms = np.zeros(4)
+        self._chk(self.L.galcamb_multi_single_cls_(C.byref(_I(ngpu)), C.byref(params), out.ctypes.data, ms.ctypes.data))
+        return out, dict(zip(("call", "prestage", "evolve", "los"), ms))
 
     def set_host_threads(self, n):
         self.L.galcamb_set_host_threads_(C.byref(_I(int(n))))

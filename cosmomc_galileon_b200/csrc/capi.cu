@@ -4,14 +4,19 @@
 // the running minimum used by Thermo_OpacityToTime, the BessRanges grid of camb/bessels.f90:68-76 and the
 // work-item ordering of the per-k kernel.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/galcamb.h"
@@ -26,9 +31,9 @@ extern "C" cudaError_t gc_set_bess_regions(const GcRegions*);
 extern "C" cudaError_t gc_launch_bessels(double2*, const double*, const int*, double*, int, int, cudaStream_t);
 extern "C" cudaError_t gc_launch_spline_k(const DevModel*, int, int, cudaStream_t);
 extern "C" cudaError_t gc_launch_los(const DevModel*, int, int, int, int, const double2*, const double*, const int*, int, int,
-                                     unsigned long long*, cudaStream_t);
+                                     unsigned long long*, int, cudaStream_t);
 extern "C" cudaError_t gc_launch_zero_delta(const DevModel*, int, int, cudaStream_t);
-extern "C" cudaError_t gc_launch_cls(const DevModel*, int, const int*, int, int, int, const double*, int, cudaStream_t);
+extern "C" cudaError_t gc_launch_cls(const DevModel*, int, const int*, int, int, int, const double*, int, int, cudaStream_t);
 extern "C" cudaError_t gc_launch_lens_ltab(double4*, double4*, int, cudaStream_t);
 extern "C" cudaError_t gc_launch_lensing(const DevModel*, int, const int*, double, const double4*, const double4*, const double*,
                                          const double*, int, double4*, const float*, double*, int*, double*, cudaStream_t);
@@ -99,6 +104,12 @@ struct Ctx {
   double* d_ws = nullptr;       // integrator workspace of the lane-per-item form (large batches)
   size_t ws_cap = 0;
   int k1_form = 0;              // which form of K1 the last call used: 0 = eight lanes per item, 1 = lane per item
+  // one spectrum shared by several devices (galcamb_multi_single_cls_): this device takes the source wavenumbers
+  // kk % kshard_world == kshard_rank, the integration wavenumbers [q_lo, q_hi), and only the sums of the C_l stage
+  int kshard_rank = 0, kshard_world = 1;
+  int q_lo = 0, q_hi = -1;      // q_hi < 0: the whole grid
+  int cls_what = 3;             // gc_launch_cls: 1 = sums over q, 2 = interpolation in l, 3 = both
+  unsigned long tmpl_version = 0;
   int num_sms = 0;
   unsigned long long* d_counters = nullptr;  // [0..2] evolve, [3] n_iter
   std::vector<int2> items;
@@ -108,7 +119,16 @@ struct Ctx {
   std::string err;
 };
 
-Ctx g;
+// One context per device.  A host thread works on the context of the device it last named in galcamb_init_ /
+// galcamb_select_device_ (thread-local), so several host threads -- OpenMP threads of a Fortran host, the workers of
+// the galcamb_multi_* entry points -- can drive one GPU each from the same process.  Calls on one context are not
+// re-entrant (like CAMB's own module state, camb/cmbmain.f90:7-8).
+std::mutex g_ctx_mutex;
+std::map<int, Ctx*> g_ctxs;
+Ctx g_none;  // what a thread sees before it has named a device: never ready
+thread_local Ctx* tl_ctx = nullptr;
+inline Ctx& cur_ctx() { return tl_ctx ? *tl_ctx : g_none; }
+#define g (cur_ctx())
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -210,11 +230,24 @@ const char* galcamb_last_error_(void) { return g.err.c_str(); }
 int galcamb_sizeof_model_(void) { return (int)sizeof(galcamb_model); }
 
 int galcamb_init_(const int* device) {
-  if (g.ready) return 0;
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    return fail(100, "galcamb_init_: no CUDA device (this library has no CPU fallback)");
-  g.device = device ? *device : 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_none.err = "galcamb_init_: no CUDA device (this library has no CPU fallback)";
+    return 100;
+  }
+  const int dev = device ? *device : 0;
+  if (dev < 0 || dev >= ndev) {
+    g_none.err = "galcamb_init_: no such device";
+    return 5;
+  }
+  {  // the calling thread works on this device's context from now on
+    std::lock_guard<std::mutex> lk(g_ctx_mutex);
+    Ctx*& c = g_ctxs[dev];
+    if (!c) c = new Ctx();
+    tl_ctx = c;
+  }
+  if (g.ready) return 0;
+  g.device = dev;
   CK(cudaSetDevice(g.device));
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   for (auto& e : g.ev) CK(cudaEventCreate(&e));
@@ -226,6 +259,18 @@ int galcamb_init_(const int* device) {
   CK(cudaMalloc((void**)&g.d_nu_tab, (size_t)GC_NRHOPN * 6 * sizeof(double)));
   CK(cudaDeviceSetLimit(cudaLimitStackSize, 8192));
   g.ready = true;
+  return 0;
+}
+
+// the calling thread switches to the (already initialised) context of another device
+int galcamb_select_device_(const int* device) {
+  std::lock_guard<std::mutex> lk(g_ctx_mutex);
+  auto it = g_ctxs.find(*device);
+  if (it == g_ctxs.end() || !it->second->ready) {
+    g_none.err = "galcamb_select_device_: device not initialised";
+    return 5;
+  }
+  tl_ctx = it->second;
   return 0;
 }
 
@@ -248,7 +293,7 @@ void galcamb_free_(void) {
     if (p) cudaFree(p);
   for (auto& e : g.ev) cudaEventDestroy(e);
   cudaStreamDestroy(g.stream);
-  g = Ctx();
+  g = Ctx();  // the context object stays registered for its device; a later galcamb_init_ sets it up again
 }
 
 int galcamb_sync_(void) {
@@ -309,8 +354,24 @@ int galcamb_get_bessels_(int* nx, double* xs, double* ajl, double* ajlpr) {
   return 0;
 }
 
+// host copies of the templates: the workers of galcamb_multi_* bring their device's context up to date from here
+struct SharedTemplates {
+  std::mutex mu;
+  std::vector<double> tmpl, pp;
+  int lmax_tmpl = 0, lmax_pp = 0;
+  unsigned long version = 0;
+} g_shared_tmpl;
+
 int galcamb_set_template_(const double* tmpl, const int* lmax_tmpl) {
   if (!g.ready) return fail(100, "not initialised");
+  {
+    std::lock_guard<std::mutex> lk(g_shared_tmpl.mu);
+    const bool on = tmpl && *lmax_tmpl >= 2;
+    g_shared_tmpl.tmpl.assign(on ? tmpl : nullptr, on ? tmpl + (size_t)3 * (*lmax_tmpl - 1) : nullptr);
+    g_shared_tmpl.lmax_tmpl = on ? *lmax_tmpl : 0;
+    g_shared_tmpl.version++;
+    g.tmpl_version = g_shared_tmpl.version;
+  }
   CK(cudaSetDevice(g.device));
   if (g.d_tmpl) cudaFree(g.d_tmpl);
   g.d_tmpl = nullptr;
@@ -325,6 +386,14 @@ int galcamb_set_template_(const double* tmpl, const int* lmax_tmpl) {
 
 int galcamb_set_lensing_template_(const double* pp, const int* lmax_tmpl) {
   if (!g.ready) return fail(100, "not initialised");
+  {
+    std::lock_guard<std::mutex> lk(g_shared_tmpl.mu);
+    const bool on = pp && *lmax_tmpl >= 2;
+    g_shared_tmpl.pp.assign(on ? pp : nullptr, on ? pp + (size_t)(*lmax_tmpl - 1) : nullptr);
+    g_shared_tmpl.lmax_pp = on ? *lmax_tmpl : 0;
+    g_shared_tmpl.version++;
+    g.tmpl_version = g_shared_tmpl.version;
+  }
   CK(cudaSetDevice(g.device));
   if (g.d_tmpl_pp) cudaFree(g.d_tmpl_pp);
   g.d_tmpl_pp = nullptr;
@@ -557,7 +626,7 @@ int galcamb_evolve_sources_(void) {
   //    every lane busy in the scalar part of the right-hand side -- the choice for large parameter batches.
   // Measured crossover on config 2: ~100 models (20 000 items; 48 models 1.12 s vs 128 models 1.81 s).
   long total_items = 0;
-  for (auto& s : g.slots) total_items += s.host.nk;
+  for (auto& s : g.slots) total_items += (s.host.nk + g.kshard_world - 1) / g.kshard_world;
   static long octet_items = -1;
   if (octet_items < 0) {
     const char* e = getenv("GALCAMB_OCTET_ITEMS");  // experiment knob: item count up to which the eight-lane form is used
@@ -585,6 +654,7 @@ int galcamb_evolve_sources_(void) {
     std::vector<std::pair<double, int>> order;
     for (int kk = 0; kk < max_nk; kk++) {
       order.clear();
+      if (kk % g.kshard_world != g.kshard_rank) continue;
       for (int m = 0; m < nm; m++)
         if (kk < g.slots[m].host.nk) order.emplace_back(sort_items ? slot_k(g.slots[m], kk) : 0.0, m);
       if (sort_items) std::stable_sort(order.begin(), order.end());
@@ -604,6 +674,7 @@ int galcamb_evolve_sources_(void) {
     for (int kk = 0; kk < max_nk; kk++) {
       int in_group = 0;
       order.clear();
+      if (kk % g.kshard_world != g.kshard_rank) continue;
       for (int m = 0; m < nm; m++)
         if (kk < g.slots[m].host.nk) order.emplace_back(sort_items ? slot_k(g.slots[m], kk) : 0.0, m);
       if (sort_items) std::stable_sort(order.begin(), order.end());
@@ -704,7 +775,11 @@ int galcamb_los_integrate_(void) {
   CK(cudaEventRecord(g.ev[3], g.stream));
   CK(gc_launch_zero_delta(g.d_models, nm, g.nl, g.stream));
   CK(cudaMemsetAsync(g.d_counters + 3, 0, sizeof(unsigned long long), g.stream));
-  CK(gc_launch_los(g.d_models, nm, max_nq, max_nt, S, g.d_bess, g.d_xs, g.d_ls, g.nx, g.nl, g.d_counters + 3, g.stream));
+  {
+    const int q_lo = g.q_hi >= 0 ? g.q_lo : 0, q_n = g.q_hi >= 0 ? std::max(0, std::min(g.q_hi, max_nq) - g.q_lo) : max_nq;
+    if (q_n > 0)
+      CK(gc_launch_los(g.d_models, nm, q_n, max_nt, S, g.d_bess, g.d_xs, g.d_ls, g.nx, g.nl, g.d_counters + 3, q_lo, g.stream));
+  }
   CK(cudaEventRecord(g.ev[4], g.stream));
   unsigned long long c = 0;
   CK(cudaMemcpyAsync(&c, g.d_counters + 3, sizeof c, cudaMemcpyDeviceToHost, g.stream));
@@ -728,7 +803,7 @@ int galcamb_scalar_cls_(void) {
     if (s.lmax != lmax || s.ntype != ntype) return fail(5, "all models of a batch must share lmax and source count");
   if (g.nl > 512) return fail(5, "nl > 512 not supported");
   CK(cudaEventRecord(g.ev[5], g.stream));
-  CK(gc_launch_cls(g.d_models, nm, g.d_ls, g.nl, ntype, lmax, g.d_tmpl, g.lmax_tmpl, g.stream));
+  CK(gc_launch_cls(g.d_models, nm, g.d_ls, g.nl, ntype, lmax, g.d_tmpl, g.lmax_tmpl, g.cls_what, g.stream));
   CK(cudaEventRecord(g.ev[6], g.stream));
   CK(cudaStreamSynchronize(g.stream));
   float ms = 0;
@@ -906,8 +981,10 @@ int galcamb_batch_upload_(const galcamb_model* models, const int* nmodels) {
   std::vector<std::string> errs(nth);
   std::vector<std::thread> pool;
   std::atomic<int> next(0);
+  Ctx* const parent = tl_ctx;
   for (int t = 0; t < nth; t++)
     pool.emplace_back([&, t]() {
+      tl_ctx = parent;          // the workers pack into the slots of the caller's context
       cudaSetDevice(g.device);  // pinned-buffer growth inside pack_model
       for (;;) {
         const int i = next.fetch_add(1);
@@ -1042,6 +1119,272 @@ int galcamb_get_evolve_stats_(double* s) {
 
 int galcamb_get_counters_(double* c) {
   for (int i = 0; i < 4; i++) c[i] = g.counters[i];
+  return 0;
+}
+
+// ================================================================================================ several GPUs, one process
+// SURVEY.md section 8e behind the C ABI: a Fortran host (or any single process) reaches every GPU of the box through
+// these two calls.  One worker thread per device drives that device's context.
+//   * galcamb_multi_params_to_cls_ : parameter-batch sharding.  The points are pre-staged once on the host threads, the
+//     valid ones are dealt to the devices in contiguous blocks, every device runs stages 1-4 on its block and writes its
+//     C_l rows straight into the caller's array -- the path has no data exchange between devices at all.
+//   * galcamb_multi_single_cls_    : ONE spectrum shared by the devices (the chain-step call).  Source wavenumbers are
+//     dealt round-robin in cost order (kk mod G; low k = long integrations first, camb/cmbmain.f90:201), the Src rows
+//     are merged with an NCCL all-reduce over NVLink (the one coupling of the k loop, camb/cmbmain.f90:1274: the spline
+//     along k needs every k), every device integrates a slice of the ~2700 integration wavenumbers (:263-267) and forms
+//     the partial sums of C_l over its slice, a second all-reduce of iCl (nl x ntype doubles) completes them.
+// NCCL is loaded at run time (libnccl.so.2) the first time the second call is used with more than one device.
+namespace {
+
+struct NcclApi {
+  void* h = nullptr;
+  int (*CommInitAll)(void**, int, const int*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::vector<void*> comms;
+  bool load() {
+    if (h) return true;
+    h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+    CommInitAll = (int (*)(void**, int, const int*))dlsym(h, "ncclCommInitAll");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    return CommInitAll && AllReduce && CommDestroy;
+  }
+} g_nccl;
+const int kNcclFloat64 = 8, kNcclSum = 0;  // ncclDataType_t / ncclRedOp_t values of nccl.h
+
+// The workers agree before every collective: a device that failed must not leave the others waiting inside NCCL.
+struct Agreement {
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0, generation = 0, world;
+  bool all_ok = true, result = true;
+  explicit Agreement(int w) : world(w) {}
+  bool arrive(bool ok) {  // true iff every worker arrived with ok
+    std::unique_lock<std::mutex> lk(mu);
+    all_ok = all_ok && ok;
+    const int gen = generation;
+    if (++arrived == world) {
+      result = all_ok;
+      arrived = 0;
+      all_ok = true;
+      generation++;
+      cv.notify_all();
+      return result;
+    }
+    cv.wait(lk, [&] { return generation != gen; });
+    return result;
+  }
+};
+
+// bring the calling worker's context up to date with the templates the host registered on any context
+int sync_templates() {
+  std::vector<double> t, pp;
+  int lt = 0, lp = 0;
+  unsigned long v;
+  {
+    std::lock_guard<std::mutex> lk(g_shared_tmpl.mu);
+    v = g_shared_tmpl.version;
+    if (g.tmpl_version == v) return 0;
+    t = g_shared_tmpl.tmpl;
+    pp = g_shared_tmpl.pp;
+    lt = g_shared_tmpl.lmax_tmpl;
+    lp = g_shared_tmpl.lmax_pp;
+  }
+  // (the two setters below take the same mutex and bump the version; re-stamp afterwards)
+  if (int rc = galcamb_set_template_(t.empty() ? nullptr : t.data(), &lt)) return rc;
+  if (int rc = galcamb_set_lensing_template_(pp.empty() ? nullptr : pp.data(), &lp)) return rc;
+  return 0;
+}
+
+int set_bessels_for_point(int i, double boost) {
+  int nl = 0, kmaxfile = 0;
+  galcamb_prestage_lsamples_(&i, &nl, nullptr, &kmaxfile);
+  std::vector<int> ls(nl);
+  galcamb_prestage_lsamples_(&i, &nl, ls.data(), &kmaxfile);
+  return galcamb_set_bessels_(ls.data(), &nl, &kmaxfile, &boost);
+}
+
+}  // namespace
+
+int galcamb_device_count_(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int galcamb_multi_params_to_cls_(const int* ngpu, const galcamb_params* params, const int* n, const int* nthreads, double* Cl_out) {
+  const int G = *ngpu;
+  if (G < 1 || G > galcamb_device_count_()) {
+    g_none.err = "galcamb_multi_params_to_cls_: ngpu out of range";
+    return 5;
+  }
+  Ctx* const caller = tl_ctx;
+  const int rc_pre = galcamb_prestage_(params, n, nthreads);
+  std::vector<galcamb_model> models;
+  std::vector<int> where;
+  for (int i = 0; i < *n; i++) {
+    galcamb_model m;
+    if (galcamb_prestage_model_(&i, &m) == 0) {
+      models.push_back(m);
+      where.push_back(i);
+    }
+  }
+  const size_t per = (size_t)3 * (params[0].Max_l - 1);
+  for (size_t j = 0; j < per * (size_t)*n; j++) Cl_out[j] = std::nan("");
+  if (models.empty()) return rc_pre ? rc_pre : 5;
+  const int nm = (int)models.size();
+  const int old_threads = galcamb_get_host_threads_();
+  int per_dev_threads = std::max(1, (old_threads > 0 ? old_threads : (int)std::thread::hardware_concurrency()) / G);
+  galcamb_set_host_threads_(&per_dev_threads);
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> errs(G);
+  std::vector<std::thread> workers;
+  for (int r = 0; r < G; r++)
+    workers.emplace_back([&, r]() {
+      const int lo = (int)((long)nm * r / G), hi = (int)((long)nm * (r + 1) / G);
+      if (hi <= lo) return;
+      int rc = galcamb_init_(&r);
+      if (!rc) rc = sync_templates();
+      if (!rc) rc = set_bessels_for_point(where[lo], models[lo].AccuracyBoost);
+      const int cnt = hi - lo;
+      std::vector<double> out(per * cnt);
+      if (!rc) rc = galcamb_batch_cls_(models.data() + lo, &cnt, out.data());
+      if (rc == 0 || rc == 4)
+        for (int j = 0; j < cnt; j++) std::copy(out.begin() + per * j, out.begin() + per * (j + 1), Cl_out + per * where[lo + j]);
+      rcs[r] = rc;
+      if (rc) errs[r] = g.err;
+    });
+  for (auto& w : workers) w.join();
+  galcamb_set_host_threads_(&old_threads);
+  tl_ctx = caller;
+  for (int r = 0; r < G; r++)
+    if (rcs[r] && rcs[r] != 4) {
+      (caller ? *caller : g_none).err = "device " + std::to_string(r) + ": " + errs[r];
+      return rcs[r];
+    }
+  for (int r = 0; r < G; r++)
+    if (rcs[r]) return rcs[r];
+  return rc_pre;
+}
+
+int galcamb_multi_single_cls_(const int* ngpu, const galcamb_params* params, double* Cl_out, double* ms_out) {
+  const int G = *ngpu;
+  if (G < 1 || G > galcamb_device_count_()) {
+    g_none.err = "galcamb_multi_single_cls_: ngpu out of range";
+    return 5;
+  }
+  Ctx* const caller = tl_ctx;
+  const auto t_begin = std::chrono::steady_clock::now();
+  int one = 1, zero = 0;
+  if (int rc = galcamb_prestage_(params, &one, &one)) return rc;
+  galcamb_model m;
+  if (int rc = galcamb_prestage_model_(&zero, &m)) return rc;
+  const auto t_pre = std::chrono::steady_clock::now();
+  if (G > 1) {
+    if (!g_nccl.load()) {
+      (caller ? *caller : g_none).err = "libnccl.so.2 not found";
+      return 100;
+    }
+    if ((int)g_nccl.comms.size() != G) {
+      for (void* c : g_nccl.comms) g_nccl.CommDestroy(c);
+      g_nccl.comms.assign(G, nullptr);
+      for (int r = 0; r < G; r++) {  // every device needs a context (and a primary CUDA context) before the communicators
+        if (int rc = galcamb_init_(&r)) return rc;
+      }
+      std::vector<int> devs(G);
+      for (int r = 0; r < G; r++) devs[r] = r;
+      const int e = g_nccl.CommInitAll(g_nccl.comms.data(), G, devs.data());
+      if (e != 0) {
+        g_nccl.comms.clear();
+        (caller ? *caller : g_none).err = std::string("ncclCommInitAll: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+        return 100;
+      }
+    }
+  }
+  const size_t per = (size_t)3 * (m.lmax - 1);
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> errs(G);
+  std::vector<double> k1_ms(G, 0.0), los_ms(G, 0.0);
+  Agreement agree(G);
+  std::vector<std::thread> workers;
+  for (int r = 0; r < G; r++)
+    workers.emplace_back([&, r]() {
+      auto run = [&]() -> int {
+        int rc0 = galcamb_init_(&r);
+        if (!rc0) rc0 = sync_templates();
+        if (!rc0) rc0 = set_bessels_for_point(0, m.AccuracyBoost);
+        if (!rc0) rc0 = galcamb_batch_begin_(&one);
+        if (!rc0) rc0 = galcamb_set_model_(&zero, &m);
+        if (rc0) {  // still take part in the first agreement (everybody leaves there) so that no device waits for this one
+          if (G > 1) agree.arrive(false);
+          return rc0;
+        }
+        Ctx& c = g;
+        const DevModel& D = c.slots[0].host;
+        const size_t nsrc = (size_t)D.nk * D.SourceNum * D.nt;
+        c.kshard_rank = r;
+        c.kshard_world = G;
+        c.q_lo = (int)((long)D.nq * r / G);
+        c.q_hi = (int)((long)D.nq * (r + 1) / G);
+        c.cls_what = 1;
+        struct Restore {
+          Ctx& c;
+          ~Restore() {
+            c.kshard_rank = 0;
+            c.kshard_world = 1;
+            c.q_lo = 0;
+            c.q_hi = -1;
+            c.cls_what = 3;
+          }
+        } restore{c};
+        int rc = 0;
+        if (G > 1 && cudaMemsetAsync(D.Src, 0, nsrc * sizeof(double), c.stream) != cudaSuccess) rc = fail(100, "cudaMemsetAsync(Src)");
+        if (!rc) rc = galcamb_evolve_sources_();  // rows of the other devices' k stay zero and are summed in below
+        k1_ms[r] = c.ms[0];
+        if (G > 1) {
+          if (!agree.arrive(rc == 0)) return rc ? rc : fail(100, "another device failed");
+          const int e = g_nccl.AllReduce(D.Src, D.Src, nsrc, kNcclFloat64, kNcclSum, g_nccl.comms[r], c.stream);
+          if (e != 0) rc = fail(100, "ncclAllReduce(Src) failed");
+        }
+        if (!rc) rc = galcamb_los_integrate_();
+        los_ms[r] = c.ms[2];
+        if (!rc) rc = galcamb_scalar_cls_();  // partial sums over this device's q slice
+        if (G > 1) {
+          if (!agree.arrive(rc == 0)) return rc ? rc : fail(100, "another device failed");
+          const int e = g_nccl.AllReduce(D.iCl, D.iCl, (size_t)c.slots[0].ntype * c.nl, kNcclFloat64, kNcclSum, g_nccl.comms[r], c.stream);
+          if (e != 0) rc = fail(100, "ncclAllReduce(iCl) failed");
+        }
+        if (rc) return rc;
+        if (r == 0) {
+          c.cls_what = 2;
+          if (int rc2 = galcamb_scalar_cls_()) return rc2;
+          CK(cudaMemcpyAsync(Cl_out, D.Cl, per * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        }
+        CK(cudaStreamSynchronize(c.stream));
+        return 0;
+      };
+      rcs[r] = run();
+      if (rcs[r]) errs[r] = g.err;
+    });
+  for (auto& w : workers) w.join();
+  tl_ctx = caller;
+  const auto t_end = std::chrono::steady_clock::now();
+  if (ms_out) {  // [0] whole call, [1] host pre-stage, [2] slowest device's K1, [3] slowest device's LOS slice
+    ms_out[0] = std::chrono::duration<double, std::milli>(t_end - t_begin).count();
+    ms_out[1] = std::chrono::duration<double, std::milli>(t_pre - t_begin).count();
+    ms_out[2] = *std::max_element(k1_ms.begin(), k1_ms.end());
+    ms_out[3] = *std::max_element(los_ms.begin(), los_ms.end());
+  }
+  for (int r = 0; r < G; r++)
+    if (rcs[r]) {
+      (caller ? *caller : g_none).err = "device " + std::to_string(r) + ": " + errs[r];
+      return rcs[r];
+    }
   return 0;
 }
 

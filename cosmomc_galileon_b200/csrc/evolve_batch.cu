@@ -1352,12 +1352,10 @@ extern "C" cudaError_t gc_launch_evolve_batch(const DevModel* models, const int2
   }
   const int threads = nitems <= lat_items ? 32 : GC_EVOLVE_THREADS;
   const size_t smem = (size_t)threads * GC_LANE_STRIDE;  // lane records
-  static bool configured = false;
-  if (!configured) {
+  {  // per device and cheap: set on every launch (several devices may be driven from one process)
     cudaError_t e = cudaFuncSetAttribute(gc::evolve_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)((size_t)GC_EVOLVE_THREADS * GC_LANE_STRIDE));
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int blocks = (nitems + threads - 1) / threads;
   gc::evolve_batch_kernel<<<blocks, threads, smem, stream>>>(models, items, nitems, workspace, NV, status, counters);

@@ -195,11 +195,11 @@ __global__ void spline_k_kernel(const DevModel* __restrict__ models, int nmodels
 // a fixed order (deterministic).  Returns N_iter through a global counter.
 __global__ void __launch_bounds__(256) los_kernel(const DevModel* __restrict__ models, const double2* __restrict__ bess,
                                                   const double* __restrict__ xs, const int* __restrict__ ls, int nx, int nl,
-                                                  unsigned long long* __restrict__ n_iter_out) {
+                                                  unsigned long long* __restrict__ n_iter_out, int q_lo) {
   extern __shared__ double smem[];
   const int m = blockIdx.y;
   const DevModel& M = models[m];
-  const int q_ix = blockIdx.x;  // 0-based
+  const int q_ix = blockIdx.x + q_lo;  // 0-based; q_lo > 0: this device integrates a slice of the q grid
   if (q_ix >= M.nq) return;
   const int nt = M.nt, S = M.SourceNum, nk = M.nk;
   // shared layout (1-based time index n -> slot n-1)
@@ -479,16 +479,15 @@ extern "C" cudaError_t gc_launch_spline_k(const DevModel* models, int nmodels, i
 }
 
 extern "C" cudaError_t gc_launch_los(const DevModel* models, int nmodels, int max_nq, int max_nt, int S, const double2* bess,
-                                     const double* xs, const int* ls, int nx, int nl, unsigned long long* n_iter, cudaStream_t st) {
+                                     const double* xs, const int* ls, int nx, int nl, unsigned long long* n_iter, int q_lo,
+                                     cudaStream_t st) {
   const size_t smem = ((size_t)S * max_nt + 3 * (size_t)max_nt) * sizeof(double) + (size_t)max_nt * sizeof(int);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024) {  // per device and cheap: set on every launch (several devices may be driven from one process)
     cudaError_t e = cudaFuncSetAttribute(gc::los_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
-  dim3 g(max_nq, nmodels);
-  gc::los_kernel<<<g, 256, smem, st>>>(models, bess, xs, ls, nx, nl, n_iter);
+  dim3 g(max_nq, nmodels);  // max_nq = number of q values to integrate from q_lo on
+  gc::los_kernel<<<g, 256, smem, st>>>(models, bess, xs, ls, nx, nl, n_iter, q_lo);
   return cudaGetLastError();
 }
 
@@ -498,11 +497,16 @@ extern "C" cudaError_t gc_launch_zero_delta(const DevModel* models, int nmodels,
   return cudaGetLastError();
 }
 
+// what = 1: the sums over q (iCl), 2: the interpolation in l, 3: both
 extern "C" cudaError_t gc_launch_cls(const DevModel* models, int nmodels, const int* ls, int nl, int ntype, int lmax,
-                                     const double* tmpl, int lmax_tmpl, cudaStream_t st) {
-  dim3 g(nl, nmodels);
-  gc::cl_kernel<<<g, 256, 0, st>>>(models, ls, nl);
-  dim3 g2(ntype, nmodels);
-  gc::cl_interp_kernel<<<g2, 256, 0, st>>>(models, ls, nl, lmax, tmpl, lmax_tmpl);
+                                     const double* tmpl, int lmax_tmpl, int what, cudaStream_t st) {
+  if (what & 1) {
+    dim3 g(nl, nmodels);
+    gc::cl_kernel<<<g, 256, 0, st>>>(models, ls, nl);
+  }
+  if (what & 2) {
+    dim3 g2(ntype, nmodels);
+    gc::cl_interp_kernel<<<g2, 256, 0, st>>>(models, ls, nl, lmax, tmpl, lmax_tmpl);
+  }
   return cudaGetLastError();
 }

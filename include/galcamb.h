@@ -199,6 +199,19 @@ int galcamb_get_host_threads_(void);
  * integration rejects come back as NaN rows; Cl_out as in galcamb_batch_cls_. */
 int galcamb_params_to_cls_(const galcamb_params* params, const int* n, const int* nthreads, double* Cl_out);
 
+/* --- several GPUs from one process -------------------------------------------------------------------------------
+ * galcamb_init_ may be called once per device; a host thread works on the context of the device it named last
+ * (galcamb_init_ / galcamb_select_device_), so OpenMP threads of a Fortran host can drive one GPU each.  The two calls
+ * below do that themselves with one worker thread per device:
+ *   parameter-batch sharding: contiguous blocks of the valid points per device, no exchange between devices;
+ *   one spectrum over ngpu devices: source k-modes dealt round-robin in cost order, Src merged by an NCCL all-reduce
+ *   (the one coupling of the k loop, camb/cmbmain.f90:1274), the integration k-modes sliced, iCl all-reduced.
+ * ms (may be NULL) = {whole call, host pre-stage, slowest device's K1, slowest device's line-of-sight slice}. */
+int galcamb_device_count_(void);
+int galcamb_select_device_(const int* device);
+int galcamb_multi_params_to_cls_(const int* ngpu, const galcamb_params* params, const int* n, const int* nthreads, double* Cl_out);
+int galcamb_multi_single_cls_(const int* ngpu, const galcamb_params* params, double* Cl_out, double* ms);
+
 /* measurement hooks (bench.py): last stage durations in ms (CUDA events on the library stream) and the
  * algorithmic work counters of SURVEY.md section 8(d). */
 int galcamb_get_timings_(double* ms /*[8]: evolve, spline_k, los, cls, lensing, -, bessel, total of 0..3*/);
