@@ -150,7 +150,9 @@ int grow(T*& p, size_t& cap, size_t n) {
   return 0;
 }
 
+std::mutex g_err_mutex;  // pack_model's workers share their caller's context and may fail at the same time
 int fail(int code, const char* msg) {
+  std::lock_guard<std::mutex> lk(g_err_mutex);
   g.err = msg;
   return code;
 }
@@ -314,12 +316,18 @@ int galcamb_set_bessels_(const int* ls, const int* nl, const int* kmaxfile, cons
   GcRegions R{};
   build_bess_ranges(*kmaxfile, *AccuracyBoost, R, g.xs);
   g.ls.assign(ls, ls + n);
-  g.nl = n;
   g.nx = (int)g.xs.size();
   g.kmaxfile = *kmaxfile;
   g.bess_boost = *AccuracyBoost;
   for (void* p : {(void*)g.d_ls, (void*)g.d_xs, (void*)g.d_bess})
     if (p) cudaFree(p);
+  g.d_ls = nullptr;
+  g.d_xs = nullptr;
+  g.d_bess = nullptr;
+  const int old_nl = g.nl;
+  g.nl = 0;  // a failure below leaves the context without Bessel tables, not with dangling ones
+  if (n != old_nl)
+    for (auto& sl : g.slots) sl.set = false;  // their Delta / iCl buffers were sized for the previous l sampling
   CK(cudaMalloc((void**)&g.d_ls, n * sizeof(int)));
   CK(cudaMalloc((void**)&g.d_xs, g.nx * sizeof(double)));
   CK(cudaMalloc((void**)&g.d_bess, (size_t)g.nx * n * sizeof(double2)));
@@ -332,6 +340,7 @@ int galcamb_set_bessels_(const int* ls, const int* nl, const int* kmaxfile, cons
   CK(cudaEventRecord(g.ev[9], g.stream));
   CK(cudaStreamSynchronize(g.stream));
   cudaFree(scratch);
+  g.nl = n;
   float ms = 0;
   cudaEventElapsedTime(&ms, g.ev[8], g.ev[9]);
   g.ms[6] = ms;
@@ -433,6 +442,9 @@ static int pack_model(int islot, const galcamb_model* m) {
   if (*slot < 0 || *slot >= (int)g.slots.size()) return fail(5, "bad slot");
   if (g.nl == 0) return fail(5, "galcamb_set_bessels_ must be called first");
   if (m->Nu_mass_eigenstates > GC_MAX_NU || m->nqmax > GC_MAX_NQ) return fail(5, "too many neutrino eigenstates / q nodes");
+  if (m->nthermo < 2 || !(m->tauminn > 0) || !(m->dlntau > 0)) return fail(5, "empty or degenerate thermo table in galcamb_model");
+  if (m->use_galileon && m->ngal < 2) return fail(5, "use_galileon needs a tabulated background (ngal >= 2)");
+  if (m->Nu_mass_eigenstates > 0 && !(m->dlnam > 0)) return fail(5, "massive neutrinos need their tables (dlnam > 0)");
   if (m->n_tau_regions > GC_MAX_REGIONS) return fail(5, "too many TimeSteps regions");
   if (m->nk < 2 || m->nq < 1 || m->nt < 2 || m->lmax < 2) return fail(5, "empty k, q or time grid in galcamb_model");
   Slot& s = g.slots[*slot];
@@ -802,6 +814,9 @@ int galcamb_scalar_cls_(void) {
   for (auto& s : g.slots)
     if (s.lmax != lmax || s.ntype != ntype) return fail(5, "all models of a batch must share lmax and source count");
   if (g.nl > 512) return fail(5, "nl > 512 not supported");
+  // InterpolateClArrTemplated (camb/modules.f90:1046-1089) is restated for a template that covers Max_l; its
+  // direct-interpolation tail beyond lmax_extrap_highl = 8000 is not
+  if (g.d_tmpl && (g.lmax_tmpl < lmax || lmax > 8000)) return fail(5, "high-l template shorter than Max_l (or Max_l > 8000)");
   CK(cudaEventRecord(g.ev[5], g.stream));
   CK(gc_launch_cls(g.d_models, nm, g.d_ls, g.nl, ntype, lmax, g.d_tmpl, g.lmax_tmpl, g.cls_what, g.stream));
   CK(cudaEventRecord(g.ev[6], g.stream));
@@ -835,7 +850,8 @@ int galcamb_lens_cls_(void) {
   if (lmax > Max_l && (!g.d_tmpl || !g.d_tmpl_pp || g.lmax_tmpl < lmax || g.lmax_tmpl_pp != g.lmax_tmpl))
     return fail(5, "lens_cls needs the high-L template (galcamb_set_template_ + galcamb_set_lensing_template_)");
   int ix = g.nl - 1;
-  while (g.ls[ix] > Max_l - 100) ix--;  // lensed_convolution_margin, :99-103
+  if (Max_l - 100 < g.ls[0]) return fail(5, "lens_cls: Max_l too small for the lensed_convolution_margin of 100");
+  while (ix > 0 && g.ls[ix] > Max_l - 100) ix--;  // lensed_convolution_margin, :99-103
   const int lmax_lensed = g.ls[ix];
   int npoints = (int)(Max_l * 2 * AB);
   double dtheta = pi / npoints;

@@ -73,7 +73,7 @@ typedef struct galcamb_model {
   galcamb_region tau_regions[GALCAMB_MAX_REGIONS];       /* TimeSteps%R(1:count), for Ranges_IndexOf */
   /* Galileon background owned by galileon.cc (camb/galileon.cc:72-92, :666-682) */
   double c2, c3, c4, c5, cG, h0, orad;
-  int ngal;                                               /* 30001 points */
+  int ngal;                                               /* the nb + 1 = 30 000 tabulated points (camb/galileon.cc:72) */
   const double *gal_a, *gal_h, *gal_x;                    /* ascending a; h = hbar(a); x = dpi/da */
   /* k grids */
   int nk;
