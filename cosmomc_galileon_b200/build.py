@@ -19,6 +19,7 @@ VARIANT = os.environ.get("GALCAMB_VARIANT", "")
 OBJ = os.path.join(HERE, "_build" + ("_" + VARIANT if VARIANT else ""))
 LIB = os.path.join(HERE, "libgalcamb_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 SOURCES = ["evolve.cu", "evolve_batch.cu", "los.cu", "lensing.cu", "capi.cu", "fp64_peak.cu", "galileon_host.cu", "prestage.cu"]
+TRANSFER_SOURCES = ["evolve.cu", "evolve_batch.cu"]  # also built with -DGC_WITH_TRANSFER (CP%WantTransfer)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FMAD = os.environ.get("GALCAMB_FMAD", "true")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=" + FMAD, "-std=c++17", "-Xcompiler",
@@ -38,10 +39,13 @@ def build(verbose=False, force=False):
     headers.append(os.path.join(os.path.dirname(HERE), "include", "galcamb.h"))
     headers.append(os.path.join(os.path.dirname(HERE), "include", "galileon_abi.h"))
     jobs = []
-    for s in SOURCES:
-        src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s.replace(".cu", ".o"))
+    # (source, object, extra flags): the two K1 files are compiled a second time with the matter-transfer taps
+    units = [(s, s.replace(".cu", ".o"), []) for s in SOURCES]
+    units += [(s, s.replace(".cu", "_tr.o"), ["-DGC_WITH_TRANSFER"]) for s in TRANSFER_SOURCES]
+    for s, o, extra in units:
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ, o)
         if force or _stale(obj, [src] + headers):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -53,7 +57,7 @@ def build(verbose=False, force=False):
     if verbose:
         for l in logs:
             sys.stderr.write(l)
-    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+    objs = [os.path.join(OBJ, o) for _, o, _ in units]
     if force or jobs or _stale(LIB, objs):
         subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, "-ccbin", "/usr/bin/g++"] + objs + ["-lcudart", "-ldl"])
     return LIB

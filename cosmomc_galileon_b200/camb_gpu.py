@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-MAX_NU, MAX_NQ, MAX_REGIONS = 5, 5, 16
+MAX_NU, MAX_NQ, MAX_REGIONS, MAX_TRANSFER_Z = 5, 5, 16, 16
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -51,6 +51,8 @@ class CModel(C.Structure):
         + [("nk", _I), ("k", _P), ("nq", _I), ("q", _P), ("dq", _P)]
         + [(n, _D) for n in "ScalarPowerAmp an n_run n_runrun k_0_scalar".split()]
         + [("lmax", _I)]
+        + [("WantTransfer", _I), ("transfer_num_redshifts", _I), ("tautf", _D * MAX_TRANSFER_Z), ("nk_transfer", _I),
+           ("k_transfer", _P), ("H0", _D)]
     )
 
 
@@ -70,6 +72,8 @@ class CParams(C.Structure):
                              "HighAccuracyDefault").split()]
         + [(n, _D) for n in "AccuracyBoost lSampleBoost lAccuracyBoost".split()]
         + [("use_spline_template", _I)]
+        + [(n, _I) for n in "WantTransfer transfer_high_precision transfer_k_per_logint transfer_num_redshifts".split()]
+        + [("transfer_kmax", _D), ("transfer_redshifts", _D * MAX_TRANSFER_Z)]
     )
 
 
@@ -91,7 +95,7 @@ def make_params(ombh2=None, omch2=None, omnuh2=None, **kw):
     for k, v in kw.items():
         if k not in names:
             raise KeyError("galcamb_params has no field %r" % k)
-        if k.startswith("Nu_mass_") and k != "Nu_mass_eigenstates":
+        if (k.startswith("Nu_mass_") and k != "Nu_mass_eigenstates") or k == "transfer_redshifts":
             arr = getattr(p, k)
             for i, x in enumerate(v):
                 arr[i] = x
@@ -149,8 +153,14 @@ class ModelTables:
         m = CModel()
         d = self.d
         for n in SCALARS:
-            if n != "n_tau_regions":
+            if n in ("WantTransfer", "transfer_num_redshifts", "nk_transfer", "H0"):  # absent from older fixtures
+                setattr(m, n, d.get(n, 0))
+            elif n != "n_tau_regions":
                 setattr(m, n, d[n])
+        tf = np.zeros(MAX_TRANSFER_Z)
+        a = np.atleast_1d(d.get("tautf", []))
+        tf[: len(a)] = a[:MAX_TRANSFER_Z]
+        m.tautf = (_D * MAX_TRANSFER_Z)(*tf)
         for n in ARRAYS:
             a = d.get(n)
             setattr(m, n, a.ctypes.data_as(_P) if a is not None and a.size else None)
@@ -212,6 +222,7 @@ def load_library():
         L.galcamb_get_cls_.argtypes = [C.POINTER(_I), C.c_void_p, C.c_void_p]
         L.galcamb_put_cls_.argtypes = [C.POINTER(_I), C.c_void_p]
         L.galcamb_get_status_.argtypes = [C.POINTER(_I), C.POINTER(_I)]
+        L.galcamb_get_transfer_.argtypes = [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.c_void_p, C.c_void_p, C.c_void_p]
         L.galcamb_batch_cls_.argtypes = [C.POINTER(CModel), C.POINTER(_I), C.c_void_p]
         L.galcamb_batch_lensed_cls_.argtypes = [C.POINTER(CModel), C.POINTER(_I), C.c_void_p, C.POINTER(_I), C.c_void_p]
         L.galcamb_set_primordial_.argtypes = [C.POINTER(_I)] + [C.POINTER(_D)] * 5
@@ -274,7 +285,7 @@ def prestage(params, nthreads=0, copy=True):
         sizes = dict(nu_r1=2000, nu_p1=2000, nu_dr1=2000, nu_dp1=2000, nu_ddr1=2000, nu_ddp1=2000, cs2=m.nthermo,
                      dcs2=m.nthermo, dotmu=m.nthermo, ddotmu=m.nthermo, dddotmu=m.nthermo, tau=m.nt, dtau=m.nt, vis=m.nt,
                      dvis=m.nt, ddvis=m.nt, expmmu=m.nt, opac=m.nt, dopac=m.nt, gal_a=m.ngal, gal_h=m.ngal, gal_x=m.ngal,
-                     k=m.nk, q=m.nq, dq=m.nq)
+                     k=m.nk, q=m.nq, dq=m.nq, k_transfer=m.nk_transfer)
         for name in ARRAYS:
             ptr = getattr(m, name)
             if not ptr or sizes[name] == 0:
@@ -294,6 +305,7 @@ def prestage(params, nthreads=0, copy=True):
         if not ne:
             d["nqmax"] = 0
         d["tau_regions"] = np.array([[r.Low, r.High, r.delta, r.start_index, r.IsLog] for r in m.tau_regions[: m.n_tau_regions]])
+        d["tautf"] = np.array(m.tautf[: m.transfer_num_redshifts])
         d["ls"] = ls
         d["kmaxfile"] = kmax.value
         tables.append(ModelTables(d))
@@ -511,6 +523,21 @@ class GalCamb:
         ms = np.zeros(8)
         self.L.galcamb_get_timings_(ms.ctypes.data)
         return dict(zip("evolve spline_k los cls lensing unused bessel total".split(), ms))
+
+    def transfer(self, slot=0):
+        """Matter transfer functions of a slot (galcamb_get_transfer_): dict with q_trans [nq], TransferData [nz][nq][13]
+        (= Fortran TransferData(13, num_q_trans, nz), FP64) and sigma8 [nz]."""
+        nq, nz = _I(0), _I(0)
+        self._chk(self.L.galcamb_get_transfer_(C.byref(_I(slot)), C.byref(nq), C.byref(nz), None, None, None))
+        q, T, s8 = np.zeros(nq.value), np.zeros((nz.value, nq.value, 13)), np.zeros(nz.value)
+        self._chk(self.L.galcamb_get_transfer_(C.byref(_I(slot)), C.byref(nq), C.byref(nz), q.ctypes.data, T.ctypes.data,
+                                                s8.ctypes.data))
+        return dict(q_trans=q, TransferData=T, sigma8=s8)
+
+    def host_timings(self):
+        ms = np.zeros(8)
+        self.L.galcamb_get_host_timings_(ms.ctypes.data)
+        return dict(zip("pack h2d_enqueue upload stages d2h collect".split(), ms))
 
     def evolve_stats(self):
         c = np.zeros(2)

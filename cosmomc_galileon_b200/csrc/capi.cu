@@ -27,6 +27,12 @@ extern "C" cudaError_t gc_launch_evolve(const DevModel*, const int2*, int, int, 
 extern "C" int gc_evolve_warps_per_cta(int);
 extern "C" void gc_upload_constants_batch();
 extern "C" cudaError_t gc_launch_evolve_batch(const DevModel*, const int2*, int, double*, int, int*, unsigned long long*, cudaStream_t);
+// the same two kernels compiled with the matter-transfer taps (-DGC_WITH_TRANSFER): used when a model of the batch has WantTransfer
+extern "C" void gc_upload_constants_tr();
+extern "C" cudaError_t gc_launch_evolve_tr(const DevModel*, const int2*, int, int, int, unsigned*, int*, unsigned long long*, cudaStream_t);
+extern "C" int gc_evolve_warps_per_cta_tr(int);
+extern "C" void gc_upload_constants_batch_tr();
+extern "C" cudaError_t gc_launch_evolve_batch_tr(const DevModel*, const int2*, int, double*, int, int*, unsigned long long*, cudaStream_t);
 extern "C" cudaError_t gc_set_bess_regions(const GcRegions*);
 extern "C" cudaError_t gc_launch_bessels(double2*, const double*, const int*, double*, int, int, cudaStream_t);
 extern "C" cudaError_t gc_launch_spline_k(const DevModel*, int, int, cudaStream_t);
@@ -51,7 +57,7 @@ struct Slot {
   double* staging = nullptr;  // pinned host buffer (packed AoS tables)
   size_t staging_cap = 0;
   size_t total = 0, n_th = 0, n_pm = 0, n_ts = 0, n_gal = 0;
-  int m_nk = 0, m_nq = 0, m_lmax = 0;
+  int m_nk = 0, m_nq = 0, m_lmax = 0, m_nk_tr = 0;
   int ensure_staging(size_t n) {
     if (n <= staging_cap) return 0;
     if (staging) cudaFreeHost(staging);
@@ -114,6 +120,7 @@ struct Ctx {
   unsigned long long* d_counters = nullptr;  // [0..2] evolve, [3] n_iter
   std::vector<int2> items;
   double ms[8] = {0};
+  double host_ms[8] = {0};  // wall clock of the host phases of the last batch call (galcamb_get_host_timings_)
   double counters[4] = {0};
   double evolve_stats[3] = {0};
   std::string err;
@@ -255,6 +262,8 @@ int galcamb_init_(const int* device) {
   for (auto& e : g.ev) CK(cudaEventCreate(&e));
   gc_upload_constants();
   gc_upload_constants_batch();
+  gc_upload_constants_tr();
+  gc_upload_constants_batch_tr();
   CK(cudaMalloc((void**)&g.d_counters, 24 * sizeof(unsigned long long)));
   CK(cudaMalloc((void**)&g.d_queue, sizeof(unsigned)));
   CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, g.device));
@@ -447,6 +456,11 @@ static int pack_model(int islot, const galcamb_model* m) {
   if (m->Nu_mass_eigenstates > 0 && !(m->dlnam > 0)) return fail(5, "massive neutrinos need their tables (dlnam > 0)");
   if (m->n_tau_regions > GC_MAX_REGIONS) return fail(5, "too many TimeSteps regions");
   if (m->nk < 2 || m->nq < 1 || m->nt < 2 || m->lmax < 2) return fail(5, "empty k, q or time grid in galcamb_model");
+  if (m->WantTransfer && (m->transfer_num_redshifts < 1 || m->transfer_num_redshifts > GC_MAX_TF || m->nk_transfer < 0 ||
+                          (m->nk_transfer > 0 && !m->k_transfer) || !(m->H0 > 0)))
+    return fail(5, "WantTransfer needs 1..16 transfer times, H0 and the transfer wavenumbers");
+  for (int i = 1; m->WantTransfer && i < m->transfer_num_redshifts; i++)
+    if (!(m->tautf[i] > m->tautf[i - 1])) return fail(5, "Transfer redshifts not set or out of order");  // camb/cmbmain.f90:787-790
   Slot& s = g.slots[*slot];
   DevModel& D = s.host;
   D = DevModel{};
@@ -477,6 +491,11 @@ static int pack_model(int islot, const galcamb_model* m) {
   D.nt = m->nt; D.nk = m->nk; D.nq = m->nq;
   D.c2 = m->c2; D.c3 = m->c3; D.c4 = m->c4; D.c5 = m->c5; D.cG = m->cG; D.h0 = m->h0; D.orad = m->orad;
   D.ScalarPowerAmp = m->ScalarPowerAmp; D.an = m->an; D.n_run = m->n_run; D.n_runrun = m->n_runrun; D.k_0_scalar = m->k_0_scalar;
+  D.WantTransfer = m->WantTransfer ? 1 : 0;
+  D.ntf = m->WantTransfer ? m->transfer_num_redshifts : 0;
+  D.nk_tr = m->WantTransfer ? m->nk_transfer : 0;
+  for (int i = 0; i < GC_MAX_TF; i++) D.tautf[i] = i < D.ntf ? m->tautf[i] : 0.0;
+  D.h0_100 = m->H0 / 100.0;
   D.TimeSteps.count = m->n_tau_regions;
   D.TimeSteps.npoints = m->nt;
   D.TimeSteps.Lowest = m->tau[0];
@@ -492,7 +511,7 @@ static int pack_model(int islot, const galcamb_model* m) {
   const int ngal = m->use_galileon ? m->ngal + 1 : 0;  // + the linearly extrapolated node of galileon.cc:677-679
   D.ngal = ngal;
   const size_t n_th = (size_t)m->nthermo * 5, n_pm = m->nthermo, n_ts = (size_t)m->nt * 8, n_gal = (size_t)ngal * 5;
-  const size_t total = n_th + n_pm + n_ts + n_gal + m->nk + 2 * (size_t)m->nq;
+  const size_t total = n_th + n_pm + n_ts + n_gal + m->nk + 2 * (size_t)m->nq + (size_t)D.nk_tr;
   if (s.ensure_staging(total)) return fail(100, "cudaMallocHost staging");
   double* p = s.staging;
   for (int i = 0; i < m->nthermo; i++) {
@@ -530,6 +549,8 @@ static int pack_model(int islot, const galcamb_model* m) {
   std::copy(m->k, m->k + m->nk, p); p += m->nk;
   std::copy(m->q, m->q + m->nq, p); p += m->nq;
   std::copy(m->dq, m->dq + m->nq, p); p += m->nq;
+  if (D.nk_tr) { std::copy(m->k_transfer, m->k_transfer + D.nk_tr, p); p += D.nk_tr; }
+  s.m_nk_tr = D.nk_tr;
   s.total = total; s.n_th = n_th; s.n_pm = n_pm; s.n_ts = n_ts; s.n_gal = n_gal; s.m_nk = m->nk; s.m_nq = m->nq; s.m_lmax = m->lmax;
   return 0;
 }
@@ -558,16 +579,20 @@ static int upload_model(int islot, const galcamb_model* m) {
   D.k = d; d += s.m_nk;
   D.q = d; d += s.m_nq;
   D.dq = d; d += s.m_nq;
+  D.k_tr = d; d += s.m_nk_tr;
   // ---- outputs
   const size_t n_src = (size_t)s.m_nk * D.SourceNum * m->nt, n_delta = (size_t)D.SourceNum * g.nl * s.m_nq;
   const size_t n_icl = (size_t)s.ntype * g.nl, n_cl = (size_t)s.ntype * (s.m_lmax - 1);
-  if (grow(&s.d_out, &s.out_cap, 2 * n_src + n_delta + n_icl + n_cl)) return fail(100, "cudaMalloc outputs");
+  const size_t n_tr = (size_t)D.ntf * (s.m_nk + s.m_nk_tr) * GC_TRANSFER_MAX;
+  if (grow(&s.d_out, &s.out_cap, 2 * n_src + n_delta + n_icl + n_cl + n_tr)) return fail(100, "cudaMalloc outputs");
   d = s.d_out;
   D.Src = d; d += n_src;
   D.ddSrc = d; d += n_src;
   D.Delta = d; d += n_delta;
   D.iCl = d; d += n_icl;
   D.Cl = d; d += n_cl;
+  D.Transfer = n_tr ? d : nullptr; d += n_tr;
+  if (n_tr) CK(cudaMemsetAsync(D.Transfer, 0, n_tr * sizeof(double), g.stream));
   s.set = true;
   s.status = 0;
   return 0;
@@ -609,9 +634,10 @@ int galcamb_evolve_sources_(void) {
   // cosmologies (lock-step control flow).  Low k first: those modes are integrated all the way to tau0
   // (~7600 trial steps) while k*tau > max_etak_scalar stops the high-k modes at ~800 (camb/cmbmain.f90:1034),
   // so the longest items start first and the short ones back-fill the SMs.
-  int max_nk = 0, NV = 0;
+  int max_nk = 0, max_ntr = 0, NV = 0;
   for (auto& s : g.slots) {
     max_nk = std::max(max_nk, s.host.nk);
+    max_ntr = std::max(max_ntr, s.host.nk_tr);
     const DevModel& D = s.host;
     // upper bound of nvar over k, from the two branches of GetNumEqns (camb/equations_galileon.f90:854-870)
     const double lAB = D.lAccuracyBoost;
@@ -638,14 +664,16 @@ int galcamb_evolve_sources_(void) {
   //    every lane busy in the scalar part of the right-hand side -- the choice for large parameter batches.
   // Measured crossover on config 2: ~100 models (20 000 items; 48 models 1.12 s vs 128 models 1.81 s).
   long total_items = 0;
-  for (auto& s : g.slots) total_items += (s.host.nk + g.kshard_world - 1) / g.kshard_world;
+  for (auto& s : g.slots) total_items += (s.host.nk + s.host.nk_tr + g.kshard_world - 1) / g.kshard_world;
   static long octet_items = -1;
   if (octet_items < 0) {
     const char* e = getenv("GALCAMB_OCTET_ITEMS");  // experiment knob: item count up to which the eight-lane form is used
     octet_items = e ? atol(e) : 20000;
   }
   const int NVP = NV;
-  const int warps_per_sm = gc_evolve_warps_per_cta(NVP);
+  bool want_tr = false;
+  for (auto& s : g.slots) want_tr = want_tr || s.host.WantTransfer != 0;
+  const int warps_per_sm = want_tr ? gc_evolve_warps_per_cta_tr(NVP) : gc_evolve_warps_per_cta(NVP);
   const bool batch_form = total_items > octet_items || warps_per_sm < 1;
   g.k1_form = batch_form ? 1 : 0;
   g.items.clear();
@@ -671,6 +699,13 @@ int galcamb_evolve_sources_(void) {
         if (kk < g.slots[m].host.nk) order.emplace_back(sort_items ? slot_k(g.slots[m], kk) : 0.0, m);
       if (sort_items) std::stable_sort(order.begin(), order.end());
       for (auto& om : order) g.items.push_back(make_int2(om.second, kk));
+      while (g.items.size() % 32) g.items.push_back(make_int2(-1, -1));
+    }
+    // the wavenumbers beyond the source grid (TransferOut, camb/cmbmain.f90:1164-1177): k index nk + t of their model
+    for (int t = 0; t < max_ntr; t++) {
+      if (t % g.kshard_world != g.kshard_rank) continue;
+      for (int m = 0; m < nm; m++)
+        if (t < g.slots[m].host.nk_tr) g.items.push_back(make_int2(m, g.slots[m].host.nk + t));
       while (g.items.size() % 32) g.items.push_back(make_int2(-1, -1));
     }
   } else {
@@ -701,6 +736,20 @@ int galcamb_evolve_sources_(void) {
       if (in_group)
         for (; in_group < 4; in_group++) g.items.push_back(make_int2(-1, -1));
     }
+    for (int t = 0; t < max_ntr; t++) {  // transfer-only wavenumbers (see the batch form above)
+      if (t % g.kshard_world != g.kshard_rank) continue;
+      int in_group = 0;
+      for (int m = 0; m < nm; m++) {
+        if (t >= g.slots[m].host.nk_tr) continue;
+        g.items.push_back(make_int2(m, g.slots[m].host.nk + t));
+        if (++in_group == ipw) {
+          for (; in_group < 4; in_group++) g.items.push_back(make_int2(-1, -1));
+          in_group = 0;
+        }
+      }
+      if (in_group)
+        for (; in_group < 4; in_group++) g.items.push_back(make_int2(-1, -1));
+    }
   }
   const int nitems = (int)g.items.size();
   const int ngroups = nitems / 4;
@@ -723,9 +772,11 @@ int galcamb_evolve_sources_(void) {
   }
   CK(cudaEventRecord(g.ev[0], g.stream));
   if (batch_form) {
-    CK(gc_launch_evolve_batch(g.d_models, g.d_items, nitems, g.d_ws, NV, g.d_status, g.d_counters, g.stream));
+    CK((want_tr ? gc_launch_evolve_batch_tr : gc_launch_evolve_batch)(g.d_models, g.d_items, nitems, g.d_ws, NV, g.d_status,
+                                                                        g.d_counters, g.stream));
   } else {
-    CK(gc_launch_evolve(g.d_models, g.d_items, ngroups, NVP, g.num_sms, g.d_queue, g.d_status, g.d_counters, g.stream));
+    CK((want_tr ? gc_launch_evolve_tr : gc_launch_evolve)(g.d_models, g.d_items, ngroups, NVP, g.num_sms, g.d_queue, g.d_status,
+                                                            g.d_counters, g.stream));
   }
   CK(cudaEventRecord(g.ev[1], g.stream));
   std::vector<int> st(nitems);
@@ -978,6 +1029,61 @@ int galcamb_put_cls_(const int* slot, const double* Cl) {
   return 0;
 }
 
+// MT%TransferData (FP64) + Transfer_Get_sigmas (camb/modules.f90:2304-2370, :2450-2472: total matter, R = 8 Mpc/h,
+// trapezoid in ln k over MT%q_trans with the primordial power of the slot)
+int galcamb_get_transfer_(const int* slot, int* num_q_trans, int* num_redshifts, double* q_trans, double* TransferData,
+                          double* sigma8) {
+  if (!g.ready) return fail(100, "not initialised");
+  if (*slot < 0 || *slot >= (int)g.slots.size() || !g.slots[*slot].set) return fail(5, "bad slot");
+  CK(cudaSetDevice(g.device));
+  const Slot& s = g.slots[*slot];
+  const DevModel& D = s.host;
+  const int nqt = D.WantTransfer ? D.nk + D.nk_tr : 0, nz = D.ntf;
+  if (num_q_trans) *num_q_trans = nqt;
+  if (num_redshifts) *num_redshifts = nz;
+  if (!nqt || !nz) return 0;
+  if (q_trans) {  // the packed host copy holds both wavenumber lists (th | pmin | ts | gal | k | q | dq | k_tr)
+    const double* kk = s.staging + s.n_th + s.n_pm + s.n_ts + s.n_gal;
+    std::copy(kk, kk + D.nk, q_trans);
+    std::copy(kk + D.nk + 2 * (size_t)D.nq, kk + D.nk + 2 * (size_t)D.nq + D.nk_tr, q_trans + D.nk);
+  }
+  if (!TransferData && !sigma8) return 0;
+  const size_t n = (size_t)nz * nqt * GC_TRANSFER_MAX;
+  std::vector<double> tmp;
+  double* T = TransferData;
+  if (!T) {
+    tmp.resize(n);
+    T = tmp.data();
+  }
+  CK(cudaMemcpyAsync(T, D.Transfer, n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  if (sigma8) {
+    const double radius = 8.0, H = D.h0_100;
+    std::vector<double> dsig8o(nz, 0.0), sig8(nz, 0.0);
+    double lnko = 0;
+    for (int ik = 0; ik < nqt; ik++) {
+      const double kh = T[(size_t)ik * GC_TRANSFER_MAX];
+      if (kh == 0) continue;
+      const double k = kh * H, x = kh * radius;
+      const double win = 3 * (std::sin(x) - x * std::cos(x)) / (x * x * x);
+      const double lnk = std::log(k);
+      const double dlnk = ik == 0 ? 0.5 : lnk - lnko;
+      // ScalarPower, camb/power_tilt.f90:149-172
+      const double lnrat = std::log(k / D.k_0_scalar);
+      const double powers = D.ScalarPowerAmp * std::exp(lnrat * (D.an - 1 + lnrat * (D.n_run / 2 + D.n_runrun / 6 * lnrat)));
+      for (int iz = 0; iz < nz; iz++) {
+        const double t = T[((size_t)iz * nqt + ik) * GC_TRANSFER_MAX + 6];  // Transfer_tot
+        const double dsig8 = ((win * (k * k)) * (win * (k * k))) * powers * (t * t);
+        sig8[iz] = sig8[iz] + (dsig8 + dsig8o[iz]) * dlnk / 2;
+        dsig8o[iz] = dsig8;
+      }
+      lnko = lnk;
+    }
+    for (int iz = 0; iz < nz; iz++) sigma8[iz] = std::sqrt(sig8[iz]);
+  }
+  return 0;
+}
+
 int galcamb_get_status_(const int* slot, int* status) {
   if (*slot < 0 || *slot >= (int)g.slots.size()) return fail(5, "bad slot");
   *status = g.slots[*slot].status;
@@ -991,6 +1097,7 @@ int galcamb_batch_upload_(const galcamb_model* models, const int* nmodels) {
   if (rc) return rc;
   CK(cudaSetDevice(g.device));
   const int n = *nmodels;
+  const auto t_pack0 = std::chrono::steady_clock::now();
   const int hostt = galcamb_get_host_threads_();
   const int nth = std::max(1, std::min<int>(n, hostt > 0 ? hostt : (int)std::thread::hardware_concurrency()));
   std::vector<int> rcs(nth, 0);
@@ -1011,8 +1118,11 @@ int galcamb_batch_upload_(const galcamb_model* models, const int* nmodels) {
   for (auto& th : pool) th.join();
   for (int r : rcs)
     if (r) return r;
+  const auto t_pack1 = std::chrono::steady_clock::now();
   for (int i = 0; i < n; i++)
     if ((rc = upload_model(i, &models[i]))) return rc;
+  g.host_ms[0] = std::chrono::duration<double, std::milli>(t_pack1 - t_pack0).count();                            // packing
+  g.host_ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pack1).count();  // H2D enqueue
   return 0;
 }
 
@@ -1034,8 +1144,10 @@ int galcamb_prestaged_upload_(void) {
 
 int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* Cl_out) {
   if (!g.ready) return fail(100, "not initialised");
+  const auto t_call0 = std::chrono::steady_clock::now();
   int rc = galcamb_batch_upload_(models, nmodels);
   if (rc) return rc;
+  const auto t_call1 = std::chrono::steady_clock::now();
   // A parameter point whose integration fails (CAMB error_evolution) must not sink the batch: its slot keeps the
   // error id (galcamb_get_status_), its C_l come back as NaN, the other points are unaffected (CosmoMC rejects
   // such points one by one, source/Calculator_CAMB.f90:235-243).
@@ -1043,10 +1155,14 @@ int galcamb_batch_cls_(const galcamb_model* models, const int* nmodels, double* 
   if (rc_ev != 0 && rc_ev != 4) return rc_ev;
   if ((rc = galcamb_los_integrate_())) return rc;
   if ((rc = galcamb_scalar_cls_())) return rc;
+  const auto t_call2 = std::chrono::steady_clock::now();
   const size_t per = (size_t)3 * (models[0].lmax - 1);
   for (int i = 0; i < *nmodels; i++)
     CK(cudaMemcpyAsync(Cl_out + per * i, g.slots[i].host.Cl, per * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
+  g.host_ms[2] = std::chrono::duration<double, std::milli>(t_call1 - t_call0).count();                            // upload, whole
+  g.host_ms[3] = std::chrono::duration<double, std::milli>(t_call2 - t_call1).count();                            // stages 1-4
+  g.host_ms[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call2).count();  // D2H
   for (int i = 0; i < *nmodels; i++)
     if (g.slots[i].status)
       for (size_t j = 0; j < per; j++) Cl_out[per * i + j] = std::nan("");
@@ -1060,6 +1176,7 @@ int galcamb_prestaged_to_cls_(double* Cl_out) {
   if (!g.ready) return fail(100, "not initialised");
   const int n = galcamb_prestage_count_();
   if (n < 1) return fail(5, "no pre-staged batch");
+  const auto t_col0 = std::chrono::steady_clock::now();
   std::vector<galcamb_model> models;
   std::vector<int> where;
   for (int i = 0; i < n; i++) {
@@ -1081,6 +1198,7 @@ int galcamb_prestaged_to_cls_(double* Cl_out) {
     if (int rc = galcamb_set_bessels_(ls.data(), &nl, &kmaxfile, &boost)) return rc;  // returns at once when cached
   }
   const int nm = (int)models.size();
+  g.host_ms[5] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_col0).count();
   if (nm == n) return galcamb_batch_cls_(models.data(), &nm, Cl_out);
   std::vector<double> out(per * nm);
   const int rc = galcamb_batch_cls_(models.data(), &nm, out.data());
@@ -1124,6 +1242,14 @@ int galcamb_batch_lensed_cls_(const galcamb_model* models, const int* nmodels, d
 int galcamb_get_timings_(double* ms) {
   for (int i = 0; i < 8; i++) ms[i] = g.ms[i];
   ms[7] = g.ms[0] + g.ms[1] + g.ms[2] + g.ms[3];  // the unlensed path; ms[4] = lensing
+  return 0;
+}
+
+// wall clock of the host-side phases of the last galcamb_batch_cls_ call [ms]: 0 table packing on the host threads,
+// 1 H2D enqueue, 2 upload as a whole, 3 device stages 1-4 (incl. their host set-up), 4 D2H of the C_l,
+// 5 the collection of the pre-staged models in galcamb_prestaged_to_cls_
+int galcamb_get_host_timings_(double* ms) {
+  for (int i = 0; i < 8; i++) ms[i] = g.host_ms[i];
   return 0;
 }
 

@@ -31,6 +31,17 @@
 #include <cstddef>
 #include <cstdio>
 
+// -DGC_WITH_TRANSFER compiles this file a second time with the matter-transfer taps of CP%WantTransfer
+// (camb/cmbmain.f90:1017-1068, :1151-1201) in the control flow, in its own namespace and under entry-point names ending
+// in _tr: the default kernels stay exactly as they are without the taps (the extra state-machine phases cost registers
+// in the hot loop: +14 % on a 1024-point batch when compiled in unconditionally).
+#ifdef GC_WITH_TRANSFER
+#define gc gc_tr
+#define GC_ENTRY(name) name##_tr
+#else
+#define GC_ENTRY(name) name
+#endif
+
 #include "evolve_device.cuh"
 
 #define GC_OCT 8    // lanes per work item
@@ -55,7 +66,9 @@ namespace gc {
   } while (0)
 #endif
 
-enum Phase : int { PH_NEXT_OUTPUT = 0, PH_EVOLVE, PH_DO_SWITCH, PH_DV_ENTER, PH_DV_STEP, PH_DV_FINAL, PH_OUT_MARK, PH_DONE };
+// PH_TF_CHECK = label 101 of camb/cmbmain.f90:1049 (is a transfer redshift due before the next time step?),
+// PH_TF_ARRIVED = at (or within 1e-5 of) a transfer time: outtransf
+enum Phase : int { PH_NEXT_OUTPUT = 0, PH_EVOLVE, PH_DO_SWITCH, PH_DV_ENTER, PH_DV_STEP, PH_DV_FINAL, PH_OUT_MARK, PH_TF_CHECK, PH_TF_ARRIVED, PH_DONE };  // the two PH_TF phases: -DGC_WITH_TRANSFER only
 
 // per-equation descriptor: type | l << 4 | (iq-1) << 12 | nu_i << 16 ; type 0 = written by the scalar part
 enum EqType : unsigned {
@@ -74,6 +87,11 @@ struct Item {
   int req;  // 0 = idle/finished, 1 = trial step, 2 = single evaluation (explicit y' of a pending output)
   int ysel;  // which of the two state columns holds y (the other one is the stage input / trial solution)
   int ynorm_valid, out_pending, out_j;
+#ifdef GC_WITH_TRANSFER
+  // matter transfer functions: next transfer redshift (0-based), kind of the stop being integrated to (0 none, 1 in the
+  // time-step loop: taken if within 1e-5, 2 before the loop / transfer-only wavenumber: always taken)
+  int itf, tf_stop;
+#endif
   double tau, tauend, target;
   // dverk communication (c(13), c(14), c(17), c(18), c(19), c(20), c(21), c(23))
   double hmin, hmag, xtrial, htrial, est, c20, c21, nfail;
@@ -830,6 +848,24 @@ __device__ __noinline__ void advance(const ItemMem m) {
   for (;;) {
     switch (L.phase) {
       case PH_NEXT_OUTPUT: {
+#ifdef GC_WITH_TRANSFER
+        if (e.TransferOnly) {  // GetTransfer, camb/cmbmain.f90:1195-1199: through the transfer times only
+          if (L.itf >= M.ntf) {
+            L.phase = PH_DONE;
+            return;
+          }
+          L.tauend = M.tautf[L.itf];
+          L.tf_stop = 2;
+          L.phase = PH_EVOLVE;
+          break;
+        }
+        if (M.WantTransfer && L.j == 1 && L.itf < M.ntf && M.ts[8] > M.tautf[L.itf]) {  // :1022-1029
+          L.tauend = M.tautf[L.itf];
+          L.tf_stop = 2;
+          L.phase = PH_EVOLVE;
+          break;
+        }
+#endif
         const int jn = L.j + 1;
         const bool stops = jn > M.nt;
         double tauend = 0;
@@ -837,6 +873,9 @@ __device__ __noinline__ void advance(const ItemMem m) {
         if (!stops) {
           tauend = M.ts[(size_t)(jn - 1) * 8];
           zero = (e.q * tauend > M.max_etak_scalar && tauend > M.taurend) && !M.WantLateTime;  // camb/cmbmain.f90:1034-1036
+#ifdef GC_WITH_TRANSFER
+          zero = zero && (!M.WantTransfer || L.tau > M.tautf[M.ntf - 1]);
+#endif
         }
         if ((stops || zero) && L.out_pending) {  // no further step from this state: evaluate y' for the output now
           L.req = 2;
@@ -968,7 +1007,11 @@ __device__ __noinline__ void advance(const ItemMem m) {
             L.ind = 3;
             L.c20 = L.target;
             L.c21 = 1.0;
+#ifdef GC_WITH_TRANSFER
+            L.phase = L.after_switch ? PH_DO_SWITCH : (L.tf_stop ? PH_TF_ARRIVED : PH_OUT_MARK);
+#else
             L.phase = L.after_switch ? PH_DO_SWITCH : PH_OUT_MARK;
+#endif
             break;
           }
         } else {
@@ -988,9 +1031,45 @@ __device__ __noinline__ void advance(const ItemMem m) {
         L.n_out++;
         L.n_derivs++;  // the derivs call of output(), camb/equations_galileon.f90:1297
         L.sum_n += (unsigned)e.neq;
+#ifdef GC_WITH_TRANSFER
+        L.phase = (M.WantTransfer && L.itf < M.ntf) ? PH_TF_CHECK : PH_NEXT_OUTPUT;
+#else
         L.phase = PH_NEXT_OUTPUT;
+#endif
         break;
       }
+#ifdef GC_WITH_TRANSFER
+      case PH_TF_CHECK: {  // camb/cmbmain.f90:1049-1056
+        if (!(M.WantTransfer && L.itf < M.ntf)) {
+          L.phase = PH_NEXT_OUTPUT;
+          break;
+        }
+        const double ttf = M.tautf[L.itf];
+        if (L.j < M.nt && M.ts[(size_t)(L.j - 1) * 8] < ttf && M.ts[(size_t)L.j * 8] > ttf) {
+          L.tauend = ttf;
+          L.tf_stop = 1;
+          L.phase = PH_EVOLVE;
+          break;
+        }
+        L.tf_stop = 1;
+        L.phase = PH_TF_ARRIVED;
+        break;
+      }
+      case PH_TF_ARRIVED: {  // camb/cmbmain.f90:1026, :1059-1066, :1198 -> outtransf
+        const int kind = L.tf_stop;
+        L.tf_stop = 0;
+        bool again = false;
+        if (kind == 2 || fabs(L.tau - M.tautf[L.itf]) < 1.e-5) {
+          transfer_outputs(L.M, &e, m.Y(), L.tau, M.Transfer + ((size_t)L.itf * (M.nk + M.nk_tr) + L.kidx) * GC_TRANSFER_MAX);
+          L.n_derivs++;  // the derivs call of outtransf, camb/equations_galileon.f90:2090
+          L.sum_n += (unsigned)e.neq;
+          L.itf++;
+          if (kind == 1 && L.j < M.nt && L.itf < M.ntf && M.ts[(size_t)L.j * 8] > M.tautf[L.itf]) again = true;
+        }
+        L.phase = again ? PH_TF_CHECK : PH_NEXT_OUTPUT;
+        break;
+      }
+#endif
       default:
         return;
     }
@@ -1013,7 +1092,15 @@ __device__ __noinline__ void init_item(const ItemMem m, const DevModel* models, 
   L.out_j = 0;
   L.ynorm = L.ynorm_new = L.errn = 0;
   L.win_i0 = -1000;
+#ifdef GC_WITH_TRANSFER
+  L.itf = 0;
+  L.tf_stop = 0;
+  // k indices beyond the source grid are the transfer-only wavenumbers (camb/cmbmain.f90:1164-1177)
+  L.e.TransferOnly = kidx >= M.nk;
+  L.e.q = L.e.TransferOnly ? M.k_tr[kidx - M.nk] : M.k[kidx];
+#else
   L.e.q = M.k[kidx];
+#endif
   L.e.pig = 0;
   L.e.pigdot = 0;
   for (int i = 0; i < GC_MAX_NU; i++) {
@@ -1055,7 +1142,10 @@ __device__ __noinline__ void init_item(const ItemMem m, const DevModel* models, 
   L.hmin = 0;
   L.htrial = 0;
   // Src(:,:,1) = 0 (never written by the time loop, camb/cmbmain.f90:1031)
-  for (int s = 0; s < M.SourceNum; s++) M.Src[(size_t)s * M.nk + kidx] = 0;
+#ifdef GC_WITH_TRANSFER
+  if (!L.e.TransferOnly)
+#endif
+    for (int s = 0; s < M.SourceNum; s++) M.Src[(size_t)s * M.nk + kidx] = 0;
   L.phase = PH_NEXT_OUTPUT;
 }
 
@@ -1297,6 +1387,11 @@ __global__ void __launch_bounds__(256, 1)
       L.status = 0;
       L.e.neq = 0;
       L.e.TightCoupling = false;
+#ifdef GC_WITH_TRANSFER
+      L.e.TransferOnly = false;
+      L.itf = 0;
+      L.tf_stop = 0;
+#endif
       L.ysel = 0;
       L.tau = 1.0;
       L.htrial = 0.0;
@@ -1345,7 +1440,7 @@ __global__ void __launch_bounds__(256, 1)
 
 }  // namespace gc
 
-extern "C" void gc_upload_constants() {
+extern "C" void GC_ENTRY(gc_upload_constants)() {
   double denl[260], polfac[260];
   for (int j = 0; j < 260; j++) {
     denl[j] = 1.0 / (2 * j + 1);
@@ -1356,18 +1451,18 @@ extern "C" void gc_upload_constants() {
 }
 
 // shared memory one work item needs for state vectors of up to NVP equations
-extern "C" size_t gc_evolve_item_bytes(int NVP) { return gc::item_stride_bytes(NVP); }
+extern "C" size_t GC_ENTRY(gc_evolve_item_bytes)(int NVP) { return gc::item_stride_bytes(NVP); }
 
 // warps per CTA that fit the 227 KB of one SM (one persistent CTA per SM)
-extern "C" int gc_evolve_warps_per_cta(int NVP) {
+extern "C" int GC_ENTRY(gc_evolve_warps_per_cta)(int NVP) {
   const size_t per_warp = gc::item_stride_bytes(NVP) * GC_IPW;
   int w = (int)((227 * 1024 - GC_LTAB_BYTES) / per_warp);
   return std::max(0, std::min(w, 8));
 }
 
-extern "C" cudaError_t gc_launch_evolve(const DevModel* models, const int2* groups, int ngroups, int NVP, int num_sms,
+extern "C" cudaError_t GC_ENTRY(gc_launch_evolve)(const DevModel* models, const int2* groups, int ngroups, int NVP, int num_sms,
                                         unsigned* queue, int* status, unsigned long long* counters, cudaStream_t stream) {
-  int warps = gc_evolve_warps_per_cta(NVP);
+  int warps = GC_ENTRY(gc_evolve_warps_per_cta)(NVP);
   if (warps < 1) return cudaErrorInvalidValue;
   // few groups: spread them one warp per CTA over the SMs (latency mode) before stacking warps
   const int ctas = std::min(num_sms, std::max(1, ngroups));

@@ -15,11 +15,28 @@
 #include <cstddef>
 #include <cstdio>
 
+// -DGC_WITH_TRANSFER compiles this file a second time with the matter-transfer taps of CP%WantTransfer
+// (camb/cmbmain.f90:1017-1068, :1151-1201) in the control flow, in its own namespace and under entry-point names ending
+// in _tr: the default kernels stay exactly as they are without the taps (the extra state-machine phases cost registers
+// in the hot loop: +14 % on a 1024-point batch when compiled in unconditionally).
+#ifdef GC_WITH_TRANSFER
+#define gc gc_tr
+#define GC_ENTRY(name) name##_tr
+#else
+#define GC_ENTRY(name) name
+#endif
+
 // lane-interleaved columns: element i of a column is col[(i-1)*32] (the warp touches one 256-byte line per element)
 #define GC_STRIDE 32
 #define GC_LANES 32
 #define GC_NCOL 12  // column 0 = y, columns 1..9 = dverk w(:,1..9), 10 = y of a pending output, 11 = its y'
 #include "evolve_device.cuh"
+
+// elements of a multipole hierarchy per pass: their loads are issued together, so one exposed L2 latency per pass
+#ifndef GC_HIER_UNROLL
+#define GC_HIER_UNROLL 4
+#endif
+constexpr int kHierUnroll = GC_HIER_UNROLL;
 
 namespace gc {
 
@@ -220,7 +237,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
       if (e.lmaxg > 2) {
         pigdot = denlk(e, 2) * qg - denlk2(e, 2) * y_g3 - opacity * (pig - polter) + 8.0 / 15.0 * k * sigma;
         AT(ayp, ix) = pigdot;
-#pragma unroll 4
+#pragma unroll(kHierUnroll)
         for (int l = 3; l <= e.lmaxg - 1; l++) {
           ix = ix + 1;
           AT(ayp, ix) = (denlk(e, l) * AT(ay, ix - 1) - denlk2(e, l) * AT(ay, ix + 1)) - opacity * AT(ay, ix);
@@ -234,7 +251,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
       ix = e.polind + 2;
       if (e.lmaxgpol > 2) {
         AT(ayp, ix) = -opacity * (y_e2 - polter) - k / 3.0 * y_e3;
-#pragma unroll 4
+#pragma unroll(kHierUnroll)
         for (int l = 3; l <= e.lmaxgpol - 1; l++) {
           ix = ix + 1;
           AT(ayp, ix) = -opacity * AT(ay, ix) + (denlk(e, l) * AT(ay, ix - 1) - polfack(e, l) * AT(ay, ix + 1));
@@ -259,7 +276,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
       int ix = e.r_ix + 2;
       if (e.lmaxnr > 2) {
         AT(ayp, ix) = denlk(e, 2) * qr - denlk2(e, 2) * y_r3 + 8.0 / 15.0 * k * sigma;
-#pragma unroll 4
+#pragma unroll(kHierUnroll)
         for (int l = 3; l <= e.lmaxnr - 1; l++) {
           ix = ix + 1;
           AT(ayp, ix) = (denlk(e, l) * AT(ay, ix - 1) - denlk2(e, l) * AT(ay, ix + 1));
@@ -302,7 +319,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
           AT(ayp, ind) = -AT(ayp, ind - 2) - 3 * cothxor * AT(ay, ind);
         } else {
           AT(ayp, ind) = v * (denlk(e, 2) * AT(ay, ind - 1) - denlk2(e, 2) * AT(ay, ind + 1)) + k * 8.0 / 15.0 * sigma;
-#pragma unroll 4
+#pragma unroll(kHierUnroll)
           for (int l = 3; l <= e.lmaxnu_tau[nu_i] - 1; l++) {
             ind = ind + 1;
             AT(ayp, ind) = v * (denlk(e, l) * AT(ay, ind - 1) - denlk2(e, l) * AT(ay, ind + 1));
@@ -318,7 +335,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
     int ind = e.nu_pert_ix;
     AT(ayp, ind) = +k * a2 * qr - k * AT(ay, ind + 1);
     int ind2 = e.r_ix;
-#pragma unroll 4
+#pragma unroll(kHierUnroll)
     for (int l = 1; l <= e.lmaxnu_pert - 1; l++) {
       ind = ind + 1;
       ind2 = ind2 + 1;
@@ -356,6 +373,10 @@ enum Phase : int {
   PH_OUT_MARK,
   PH_OUT_REQ,
   PH_OUT_DONE,
+#ifdef GC_WITH_TRANSFER
+  PH_TF_CHECK,    // label 101 of camb/cmbmain.f90:1049: is a transfer redshift due before the next time step?
+  PH_TF_ARRIVED,  // at (or within 1e-5 of) a transfer time: outtransf
+#endif
   PH_DONE
 };
 
@@ -390,6 +411,11 @@ struct Lane {
   // lanes' pending outputs, from y (stashed in column 10 by the next combine()), y' (column 11) and these scalars
   bool out_pending, out_stashed, flush_now, out_need_k1, stash_k1, waiting;
   int out_j, resume_phase;
+#ifdef GC_WITH_TRANSFER
+  // matter transfer functions: next transfer redshift (0-based), kind of the stop being integrated to (0 none, 1 in the
+  // time-step loop: taken if within 1e-5, 2 before the loop / transfer-only wavenumber: always taken)
+  short itf, tf_stop;
+#endif
   double out_pig, out_pigdot;
   int status;
   // work counters
@@ -876,6 +902,24 @@ __device__ __forceinline__ void advance(Lane& L, int wphase, bool align) {
   for (;;) {
     switch (L.phase) {
       case PH_NEXT_OUTPUT: {
+#ifdef GC_WITH_TRANSFER
+        if (e.TransferOnly) {  // GetTransfer, camb/cmbmain.f90:1195-1199: through the transfer times only
+          if (L.itf >= M.ntf) {
+            L.phase = PH_DONE;
+            return;
+          }
+          L.tauend = M.tautf[L.itf];
+          L.tf_stop = 2;
+          L.phase = PH_EVOLVE;
+          break;
+        }
+        if (M.WantTransfer && L.j == 1 && L.itf < M.ntf && M.ts[8] > M.tautf[L.itf]) {  // :1022-1029
+          L.tauend = M.tautf[L.itf];
+          L.tf_stop = 2;
+          L.phase = PH_EVOLVE;
+          break;
+        }
+#endif
         const int jn = L.j + 1;
         const bool stops = jn > M.nt;
         double tauend = 0;
@@ -883,6 +927,9 @@ __device__ __forceinline__ void advance(Lane& L, int wphase, bool align) {
         if (!stops) {
           tauend = M.ts[(size_t)(jn - 1) * 8];
           zero = (e.q * tauend > M.max_etak_scalar && tauend > M.taurend) && !M.WantLateTime;  // camb/cmbmain.f90:1034-1036
+#ifdef GC_WITH_TRANSFER
+          zero = zero && (!M.WantTransfer || L.tau > M.tautf[M.ntf - 1]);
+#endif
         }
         if ((stops || zero) && L.out_need_k1) {  // no further step from this state: evaluate y' for the output now
           L.resume_phase = PH_NEXT_OUTPUT;
@@ -1087,7 +1134,11 @@ __device__ __forceinline__ void advance(Lane& L, int wphase, bool align) {
             L.ind = 3;
             L.c20 = L.target;
             L.c21 = 1.0;
+#ifdef GC_WITH_TRANSFER
+            L.phase = L.after_switch ? PH_DO_SWITCH : (L.tf_stop ? PH_TF_ARRIVED : PH_OUT_MARK);
+#else
             L.phase = L.after_switch ? PH_DO_SWITCH : PH_OUT_MARK;
+#endif
             break;
           }
         } else {
@@ -1111,9 +1162,45 @@ __device__ __forceinline__ void advance(Lane& L, int wphase, bool align) {
         L.out_need_k1 = true;
         L.out_j = L.j;
         L.n_out++;
+#ifdef GC_WITH_TRANSFER
+        L.phase = (M.WantTransfer && L.itf < M.ntf) ? PH_TF_CHECK : PH_NEXT_OUTPUT;
+#else
         L.phase = PH_NEXT_OUTPUT;
+#endif
         break;
       }
+#ifdef GC_WITH_TRANSFER
+      case PH_TF_CHECK: {  // camb/cmbmain.f90:1049-1056
+        if (!(M.WantTransfer && L.itf < M.ntf)) {
+          L.phase = PH_NEXT_OUTPUT;
+          break;
+        }
+        const double ttf = M.tautf[L.itf];
+        if (L.j < M.nt && M.ts[(size_t)(L.j - 1) * 8] < ttf && M.ts[(size_t)L.j * 8] > ttf) {
+          L.tauend = ttf;
+          L.tf_stop = 1;
+          L.phase = PH_EVOLVE;
+          break;
+        }
+        L.tf_stop = 1;
+        L.phase = PH_TF_ARRIVED;
+        break;
+      }
+      case PH_TF_ARRIVED: {  // camb/cmbmain.f90:1026, :1059-1066, :1198 -> outtransf
+        const int kind = L.tf_stop;
+        L.tf_stop = 0;
+        bool again = false;
+        if (kind == 2 || fabs(L.tau - M.tautf[L.itf]) < 1.e-5) {
+          transfer_outputs(L.M, &e, col(L, 0), L.tau, M.Transfer + ((size_t)L.itf * (M.nk + M.nk_tr) + L.kidx) * GC_TRANSFER_MAX);
+          L.n_derivs++;  // the derivs call of outtransf, camb/equations_galileon.f90:2090
+          L.sum_n += e.neq;
+          L.itf++;
+          if (kind == 1 && L.j < M.nt && L.itf < M.ntf && M.ts[(size_t)L.j * 8] > M.tautf[L.itf]) again = true;
+        }
+        L.phase = again ? PH_TF_CHECK : PH_NEXT_OUTPUT;
+        break;
+      }
+#endif
       case PH_OUT_REQ: {  // explicit y' evaluation, camb/equations_galileon.f90:1296-1297
         double* yp = col(L, 11);
         for (int i = 1; i <= e.nvar; i++) AT(yp, i) = 0;
@@ -1158,6 +1245,11 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
   L.out_pending = L.out_stashed = L.flush_now = L.out_need_k1 = L.stash_k1 = L.waiting = false;
   L.resume_phase = PH_DONE;
   L.crow = -1;
+#ifdef GC_WITH_TRANSFER
+  L.itf = 0;
+  L.tf_stop = 0;
+  L.e.TransferOnly = false;
+#endif
   L.ysel = 0;
   L.ynorm_valid = false;
   L.ynorm = L.ynorm_new = L.errn = 0;
@@ -1178,7 +1270,13 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
     L.NV = NV;
     L.ws = workspace + (size_t)gwarp * GC_NCOL * NV * GC_LANES + lane;
     // DoSourcek, camb/cmbmain.f90:662-689
+#ifdef GC_WITH_TRANSFER
+    // k indices beyond the source grid are the transfer-only wavenumbers (:1164-1177)
+    L.e.TransferOnly = it.y >= M.nk;
+    L.e.q = L.e.TransferOnly ? M.k_tr[it.y - M.nk] : M.k[it.y];
+#else
     L.e.q = M.k[it.y];
+#endif
     L.e.pig = 0;
     L.e.pigdot = 0;
     for (int i = 0; i < GC_MAX_NU; i++) {
@@ -1219,7 +1317,10 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
       L.est = 0;
       L.hmin = 0;
       // Src(:,:,1) = 0 (never written by the time loop, camb/cmbmain.f90:1031)
-      for (int s = 0; s < M.SourceNum; s++) M.Src[(size_t)s * M.nk + L.kidx] = 0;
+#ifdef GC_WITH_TRANSFER
+      if (!L.e.TransferOnly)
+#endif
+        for (int s = 0; s < M.SourceNum; s++) M.Src[(size_t)s * M.nk + L.kidx] = 0;
       L.phase = PH_NEXT_OUTPUT;
     }
   }
@@ -1329,9 +1430,9 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
 
 }  // namespace gc
 
-extern "C" int gc_batch_lane_stride() { return (int)GC_LANE_STRIDE; }
+extern "C" int GC_ENTRY(gc_batch_lane_stride)() { return (int)GC_LANE_STRIDE; }
 
-extern "C" void gc_upload_constants_batch() {
+extern "C" void GC_ENTRY(gc_upload_constants_batch)() {
   double denl[260], polfac[260];
   for (int j = 0; j < 260; j++) {
     denl[j] = 1.0 / (2 * j + 1);
@@ -1341,7 +1442,7 @@ extern "C" void gc_upload_constants_batch() {
   cudaMemcpyToSymbol(c_polfac, polfac, sizeof(polfac));
 }
 
-extern "C" cudaError_t gc_launch_evolve_batch(const DevModel* models, const int2* items, int nitems, double* workspace, int NV,
+extern "C" cudaError_t GC_ENTRY(gc_launch_evolve_batch)(const DevModel* models, const int2* items, int nitems, double* workspace, int NV,
                                               int* status, unsigned long long* counters, cudaStream_t stream) {
   // Mid-size batches (up to ~800 models = 25 warps per k index): one warp per CTA, so that no warp waits for another at
   // the lock-step barrier; larger batches: 4-warp CTAs in lock step (instruction-cache sharing, see the main loop).

@@ -42,6 +42,9 @@ struct EV {
   short nu_ix[GC_MAX_NU];
   unsigned char nq[GC_MAX_NU], lmaxnu_tau[GC_MAX_NU];
   bool TightCoupling, high_ktau, no_nu, no_phot, has_nu_rel;
+#ifdef GC_WITH_TRANSFER
+  bool TransferOnly;  // a wavenumber beyond the source grid, camb/cmbmain.f90:1165
+#endif
   bool MassiveNuApprox[GC_MAX_NU], nu_nonrel[GC_MAX_NU];
   double G11[GC_MAX_NU], G30[GC_MAX_NU], MassiveNuApproxTime[GC_MAX_NU];
   double TightSwitchoffTime, pig, pigdot, poltruncfac;
@@ -453,6 +456,12 @@ __device__ inline void GetNumEqns(const DevModel& M, EV& e) {
       e.lmaxgpol = e.lmaxgpol * 2;
     }
   }
+#ifdef GC_WITH_TRANSFER
+  if (e.TransferOnly) {  // :872-875
+    e.lmaxgpol = min((int)e.lmaxgpol, (int)nintd(5 * lAB));
+    e.lmaxg = min((int)e.lmaxg, (int)nintd(6 * lAB));
+  }
+#endif
   e.poltruncfac = (double)e.lmaxgpol / max(1, (e.lmaxgpol - 2));
   SetupScalarArrayIndices(M, e, &e.nvar);
 }
@@ -761,6 +770,150 @@ static __device__ __noinline__ void output_sources(const DevModel* __restrict__ 
     }
   }
 }
+
+#ifdef GC_WITH_TRANSFER
+// ---------------------------------------------------------------- matter transfer functions
+// outtransf (camb/equations_galileon.f90:2078-2095): the transfer tap of derivs (:2325-2353) evaluated on the state y
+// at time tau; out[0..12] = TransferData(Transfer_kh .. Transfer_vel_baryon_cdm), rows 2..13 already divided by k^2.
+// Only the part of derivs above the tap is evaluated (the derivatives themselves are not needed).  During tight
+// coupling the reference reads pig before assigning it (:2331 vs :2375); 0 here and in the oracle.
+static __device__ __noinline__ void transfer_outputs(const DevModel* __restrict__ Mp, const EV* __restrict__ ep,
+                                                     const double* __restrict__ y, double tau, double* __restrict__ out) {
+  const DevModel& M = *Mp;
+  const EV& e = *ep;
+  const bool gal = M.use_galileon != 0;
+  const double k = e.k, k2 = e.k2;
+  const double a = AT(y, 1), a2 = a * a, etak = AT(y, 2), clxc = AT(y, 3), clxb = AT(y, 4), vb = AT(y, 5);
+  double dphi = 0, dphiprime = 0;
+  if (gal) {
+    dphi = AT(y, e.w_ix);
+    dphiprime = AT(y, e.w_ix + 1);
+  }
+  const double grhob_t = M.grhob / a, grhoc_t = M.grhoc / a, grhor_t = M.grhornomass / a2, grhog_t = M.grhog / a2;
+  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
+  for (int i = 0; i < M.n_eig; i++) Nu_background(M, a * M.nu_masses[i], rhonu[i], pnu[i]);
+  double xgal = 0, hbar = 0;
+  GalFast F;
+  const GalConst GC{M.c2, M.c3, M.c4, M.c5, M.cG, M.h0, M.orad};
+  if (gal) {
+    gal_HX(M, a, hbar, xgal);
+    double lam_nu = 0;
+    for (int i = 0; i < M.n_eig; i++) lam_nu += M.grhormass[i] * pnu[i];
+    gal_fast_background(GC, a, hbar, xgal, lam_nu, k, F);
+  }
+  double cs2, opacity;
+  thermo(M, tau, cs2, opacity, nullptr);
+  double grho_matter = grhob_t + grhoc_t;
+  double dgrho_matter = grhob_t * clxb + grhoc_t * clxc;
+  double dgq = grhob_t * vb;
+  double dgpi_nu = 0, grhonu = 0, dgrhonu = 0;
+  if (M.Num_Nu_massive > 0) {  // MassiveNuVars (:1209-1252) and the two outputs of MassiveNuVarsOut the tap asks for (:2335)
+    for (int nu_i = 0; nu_i < M.n_eig; nu_i++) {
+      const double grhormass_t = M.grhormass[nu_i] / a2;
+      double clxnu, qnu, dpnu, pinu;
+      if (e.MassiveNuApprox[nu_i]) {
+        clxnu = AT(y, e.nu_ix[nu_i]);
+        qnu = AT(y, e.nu_ix[nu_i] + 2);
+        pinu = AT(y, e.nu_ix[nu_i] + 3);
+      } else {
+        Nu_Integrate_L012(M, e, y, a, nu_i, clxnu, qnu, &dpnu, &pinu);
+        qnu = qnu / rhonu[nu_i];
+        clxnu = clxnu / rhonu[nu_i];
+        pinu = pinu / rhonu[nu_i];
+      }
+      const double grhonu_t = grhormass_t * rhonu[nu_i];
+      grho_matter = grho_matter + grhonu_t;
+      dgrho_matter = dgrho_matter + grhonu_t * clxnu;
+      dgq = dgq + grhonu_t * qnu;
+      grhonu = grhonu + grhonu_t;
+      dgrhonu = dgrhonu + grhonu_t * clxnu;
+      dgpi_nu = dgpi_nu + grhonu_t * pinu;
+    }
+  }
+  // dtauda(a), :107-156
+  double grhoa2;
+  if (gal && a >= 1e-10) {
+    grhoa2 = (a2 * a2) * M.grhom * (hbar * hbar);
+  } else {
+    grhoa2 = M.grhok * a2 + (M.grhoc + M.grhob) * a + M.grhog + M.grhornomass;
+    grhoa2 = grhoa2 + M.grhov * (a2 * a2);
+    if (M.Num_Nu_massive != 0)
+      for (int nu_i = 0; nu_i < M.n_eig; nu_i++) grhoa2 = grhoa2 + rhonu[nu_i] * M.grhormass[nu_i];
+  }
+  const double adotoa = 1. / (a * sqrt(3 / grhoa2));
+  double dgrho = dgrho_matter;
+  double z = 0, dz, clxr, qr, pir, clxg, qg, pig = 0, dgrhogal_t;
+  if (e.no_nu) {
+    if (gal) {
+      dgrhogal_t = gal_fast_Chigal(F, dgrho, etak, dphi, dphiprime);
+      z = (0.5 * (dgrho + dgrhogal_t) / k + etak) / adotoa;
+      dz = -adotoa * z - 0.5 * (dgrho + dgrhogal_t) / k;
+    } else {
+      z = (0.5 * dgrho / k + etak) / adotoa;
+      dz = -adotoa * z - 0.5 * dgrho / k;
+    }
+    clxr = -4 * dz / k;
+    qr = -4.0 / 3 * z;
+    pir = 0;
+  } else {
+    clxr = AT(y, e.r_ix);
+    qr = AT(y, e.r_ix + 1);
+    pir = AT(y, e.r_ix + 2);
+  }
+  if (e.no_phot) {
+    if (!e.no_nu) {
+      if (gal) {
+        dgrhogal_t = gal_fast_Chigal(F, dgrho, etak, dphi, dphiprime);
+        z = (0.5 * (dgrho + dgrhogal_t) / k + etak) / adotoa;
+        dz = -adotoa * z - 0.5 * (dgrho + dgrhogal_t) / k;
+      } else {
+        z = (0.5 * dgrho / k + etak) / adotoa;
+        dz = -adotoa * z - 0.5 * dgrho / k;
+      }
+      clxg = -4 * dz / k - 4 / k * opacity * (vb + z);
+      qg = -4.0 / 3 * z;
+    } else {
+      clxg = clxr - 4 / k * opacity * (vb + z);
+      qg = qr;
+    }
+    pig = 0;
+  } else {
+    clxg = AT(y, e.g_ix);
+    qg = AT(y, e.g_ix + 1);
+    if (!e.TightCoupling) pig = AT(y, e.g_ix + 2);
+  }
+  dgrho = dgrho + grhog_t * clxg + grhor_t * clxr;
+  dgq = dgq + grhog_t * qg + grhor_t * qr;
+  if (gal) {
+    dgrhogal_t = gal_fast_Chigal(F, dgrho, etak, dphi, dphiprime);
+    dgrho = dgrho + dgrhogal_t;
+    dgq = dgq + gal_fast_qgal(F, dgq, dphi, dphiprime);
+  }
+  z = (0.5 * dgrho / k + etak) / adotoa;
+  const double sigma = (z + 1.5 * dgq / k2);
+  double dgpi = grhor_t * pir + grhog_t * pig;
+  double clxnu_all = 0;
+  if (M.Num_Nu_massive != 0) {
+    dgpi = dgpi + dgpi_nu;
+    clxnu_all = dgrhonu / grhonu;
+  }
+  if (gal) dgpi = dgpi + gal_fast_Pigal(GC, F, dgrho, dgq, dgpi, etak, dphi);
+  const double ik2 = 1.0 / k2;
+  out[0] = k / M.h0_100;
+  out[1] = clxc * ik2;
+  out[2] = clxb * ik2;
+  out[3] = clxg * ik2;
+  out[4] = clxr * ik2;
+  out[5] = clxnu_all * ik2;
+  out[6] = (dgrho_matter / grho_matter) * ik2;
+  out[7] = ((grhob_t * clxb + grhoc_t * clxc) / (grhob_t + grhoc_t)) * ik2;
+  out[8] = (dgrho / grho_matter) * ik2;
+  out[9] = (-(dgrho + 3 * dgq * adotoa / k) / 2 - dgpi / 2) * ik2;
+  out[10] = (-k * sigma / adotoa) * ik2;
+  out[11] = (-k * (vb + sigma) / adotoa) * ik2;
+  out[12] = vb * ik2;
+}
+#endif  // GC_WITH_TRANSFER
 
 // ---------------------------------------------------------------- initial conditions
 // camb/equations_galileon.f90:1714-1928 (adiabatic mode), y = workspace column 0

@@ -21,6 +21,8 @@
 #define GC_MAX_NQ 5      // momentum nodes (nqmax <= 5 for AccuracyBoost <= 3; camb/modules.f90:1624-1627)
 #define GC_NRHOPN 2000   // camb/modules.f90:1554
 #define GC_MAX_REGIONS 16
+#define GC_MAX_TF 16      // transfer redshifts per call (GALCAMB_MAX_TRANSFER_Z; the reference allows 150, CosmoMC uses 1-4)
+#define GC_TRANSFER_MAX 13  // rows of TransferData, camb/modules.f90:1876-1884
 
 struct GcRegion {  // camb/utils.F90:8-20 (piecewise linear/log grid)
   double Low, High, delta;
@@ -74,4 +76,10 @@ struct DevModel {
   double ScalarPowerAmp, an, n_run, n_runrun, k_0_scalar;
   double* iCl;        // [ntype][nl]
   double* Cl;         // [ntype][lmax-1]
+  // matter transfer functions (camb/cmbmain.f90:508-632, :1017-1068, :1151-1201)
+  int WantTransfer, ntf, nk_tr;  // nk_tr = wavenumbers beyond the source grid (evolved through the transfer times only)
+  double tautf[GC_MAX_TF];       // conformal times of the transfer redshifts, ascending
+  double h0_100;                 // CP%h0/100 (Transfer_kh = k/h)
+  const double* k_tr;            // [nk_tr]
+  double* Transfer;              // [ntf][nk + nk_tr][13] FP64  (== Fortran TransferData(13, num_q_trans, nz))
 };

@@ -516,6 +516,8 @@ struct Model {
   double nu_tau_notmassless[GALCAMB_MAX_NQ + 1][MAXNU + 1] = {{0}}, nu_tau_nonrelativistic[MAXNU + 1] = {0}, nu_tau_massive[MAXNU + 1] = {0};
   std::vector<int> ls;  // l samples, 0-based
   int kmaxfile = 0;
+  // matter transfer functions: output times (ascending) and the wavenumbers beyond the source grid
+  std::vector<double> tautf, k_transfer;
 
   int fail(int id, const char* msg) {
     status = id;
@@ -568,6 +570,7 @@ struct Model {
   int init_vars();
   void gauge_init();
   void k_grids();
+  void transfer_grid();
   void l_samples();
   int run();
 };
@@ -960,8 +963,9 @@ int Model::init_vars() {
   dtaurec = 4 / qmax / P.AccuracyBoost;
   max_etak_scalar = P.AccuracyBoost * std::fmax(1700.0, maximum_qeta) / 20;
   if (maximum_qeta < 3500 && P.AccuracyBoost < 2) max_etak_scalar = max_etak_scalar * 1.5;
-  // GetTauStart(qmax), camb/cmbmain.f90:634-660
-  double taumin = std::fmin(0.001 / qmax, 0.1);
+  // GetTauStart(maxq), camb/cmbmain.f90:634-660, maxq of :757-762 (WantCls)
+  const double maxq = P.WantTransfer ? std::fmax(qmax, P.transfer_kmax) : qmax;
+  double taumin = std::fmin(0.001 / maxq, 0.1);
   if (Num_Nu_massive > 0) {
     double mx = 0;
     for (int i = 1; i <= Nu_mass_eigenstates; i++) mx = std::fmax(mx, nu_masses[i]);
@@ -1085,6 +1089,17 @@ int Model::init_vars() {
   ddotmu.assign(ddm.begin() + 1, ddm.end());
   dddotmu.assign(dddm.begin() + 1, dddm.end());
   gauge_init();
+  // times of the transfer-function outputs, camb/cmbmain.f90:783-793 (TimeOfz, camb/modules.f90:574-580)
+  tautf.clear();
+  if (P.WantTransfer) {
+    if (P.transfer_high_precision) return fail(5, "transfer_high_precision is not supported");
+    if (P.transfer_num_redshifts < 1 || P.transfer_num_redshifts > GALCAMB_MAX_TRANSFER_Z)
+      return fail(5, "transfer_num_redshifts out of range");
+    for (int itf = 0; itf < P.transfer_num_redshifts; itf++) {
+      tautf.push_back(std::fmin(DeltaTime(0.0, 1.0 / (P.transfer_redshifts[itf] + 1.0)), tau0));
+      if (itf > 0 && tautf[itf] <= tautf[itf - 1]) return fail(5, "Transfer redshifts not set or out of order");
+    }
+  }
   return 0;
 }
 
@@ -1151,6 +1166,53 @@ void Model::k_grids() {
   }
   q_int.get_array(true);
   kmaxfile = (int)std::fmin(maximum_qeta, Max_eta_k) + 1;  // camb/bessels.f90:44, :58
+}
+
+// InitTransfer, camb/cmbmain.f90:508-632 (flat, WantCls): the transfer wavenumber grid; kept are the values above the top
+// of the source grid, which CalcScalarSources does not visit (:597-623)
+void Model::transfer_grid() {
+  k_transfer.clear();
+  if (!P.WantTransfer) return;
+  const double kmax = P.transfer_kmax;
+  std::vector<double> qt;  // 0-based here
+  if (P.transfer_k_per_logint == 0) {
+    const double boost = P.AccuracyBoost;
+    const double q_switch_lowk1 = SP(0.7) / taurst, dlog_lowk1 = 2 * boost;
+    const double q_switch_lowk = 8 / taurst;
+    double dlog_lowk = 8 * boost;
+    if (P.HighAccuracyDefault) dlog_lowk = dlog_lowk * 2.5;
+    const double q_switch_osc = std::fmin(kmax, 30 / taurst);
+    double d_osc = 200 * boost;
+    if (P.HighAccuracyDefault) d_osc = d_osc * SP(1.8);
+    const double q_switch_highk = std::fmin(kmax, (P.HighAccuracyDefault ? 90 : 60) / taurst);
+    const double dlog_osc = 17 * boost, dlog_highk = 3 * boost, amin = 5e-5;
+    int nq = (int)(std::log(q_switch_lowk1 / amin) * dlog_lowk1) + 1;
+    for (int i = 1; i <= nq; i++) qt.push_back(amin * std::exp((i - 1) / dlog_lowk1));
+    double last = qt.back();
+    nq = (int)(std::log(q_switch_lowk / last) * dlog_lowk) + 1;
+    for (int i = 1; i <= nq; i++) qt.push_back(last * std::exp(i / dlog_lowk));
+    last = qt.back();
+    nq = (int)((q_switch_osc - last) * d_osc) + 1;
+    for (int i = 1; i <= nq; i++) qt.push_back(last + i / d_osc);
+    last = qt.back();
+    if (kmax > last) {
+      nq = (int)(std::log(q_switch_highk / last) * dlog_osc) + 1;
+      for (int i = 1; i <= nq; i++) qt.push_back(last * std::exp(i / dlog_osc));
+      last = qt.back();
+    }
+    if (kmax > last) {
+      nq = (int)(std::log(kmax / last) * dlog_highk) + 1;
+      for (int i = 1; i <= nq; i++) qt.push_back(last * std::exp(i / dlog_highk));
+    }
+  } else {
+    const int n = (int)((std::log(kmax) - std::log(qmin)) * P.transfer_k_per_logint) + 1;
+    for (int i = 1; i <= n; i++) qt.push_back(qmin * (double)std::exp((float)i / (float)P.transfer_k_per_logint));  // default-real exp
+  }
+  for (size_t i = 0; i < qt.size(); i++)
+    if (qt[i] > Evolve_q.Highest + 1e-4) {
+      k_transfer.assign(qt.begin() + i, qt.end());
+      break;
+    }
 }
 
 // camb/modules.f90:851-1008 (Log_lvalues = F)
@@ -1229,6 +1291,7 @@ int Model::run() {
   l_samples();
   if (int rc = init_vars()) return rc;
   k_grids();
+  transfer_grid();
   return 0;
 }
 
@@ -1292,6 +1355,12 @@ static void fill_view(const Model& M, galcamb_model* m) {
   m->nq = M.q_int.npoints; m->q = M.q_int.points.data() + 1; m->dq = M.q_int.dpoints.data() + 1;
   m->ScalarPowerAmp = P.ScalarPowerAmp; m->an = P.an; m->n_run = P.n_run; m->n_runrun = P.n_runrun; m->k_0_scalar = P.k_0_scalar;
   m->lmax = P.Max_l;
+  m->WantTransfer = P.WantTransfer ? 1 : 0;
+  m->transfer_num_redshifts = (int)M.tautf.size();
+  for (size_t i = 0; i < M.tautf.size() && i < GALCAMB_MAX_TRANSFER_Z; i++) m->tautf[i] = M.tautf[i];
+  m->nk_transfer = (int)M.k_transfer.size();
+  m->k_transfer = M.k_transfer.empty() ? nullptr : M.k_transfer.data();
+  m->H0 = P.H0;
 }
 
 }  // namespace pre
@@ -1309,6 +1378,7 @@ void galcamb_default_params_(galcamb_params* p) {
   p->Max_l = 2500; p->Max_eta_k = 5000; p->AccuratePolarization = 1; p->AccurateReionization = 1; p->MassiveNuMethod = 1;
   p->DoLateRadTruncation = 1; p->HighAccuracyDefault = 1; p->AccuracyBoost = 1; p->lSampleBoost = 1; p->lAccuracyBoost = 1;
   p->use_spline_template = 1;
+  p->WantTransfer = 0; p->transfer_kmax = 0.9; p->transfer_num_redshifts = 1; p->transfer_redshifts[0] = 0;
 }
 
 int galcamb_sizeof_params_(void) { return (int)sizeof(galcamb_params); }

@@ -33,6 +33,8 @@ extern "C" {
 #define GALCAMB_MAX_NU 5 /* = max_nu, camb/modules.f90:63 */
 #define GALCAMB_MAX_NQ 5
 #define GALCAMB_MAX_REGIONS 16
+#define GALCAMB_MAX_TRANSFER_Z 16 /* transfer redshifts per call (reference: max_transfer_redshifts = 150, camb/modules.f90:64) */
+#define GALCAMB_TRANSFER_MAX 13   /* rows of TransferData, camb/modules.f90:1876-1884 */
 
 /* One region of a Ranges grid (camb/utils.F90:8-20). */
 typedef struct galcamb_region {
@@ -83,6 +85,13 @@ typedef struct galcamb_model {
   /* primordial power, camb/power_tilt.f90:60-92 */
   double ScalarPowerAmp, an, n_run, n_runrun, k_0_scalar;
   int lmax;                                               /* CP%Max_l */
+  /* matter transfer functions (CP%WantTransfer): output times tautf (camb/cmbmain.f90:783-793, ascending) and the
+   * wavenumbers InitTransfer appends beyond the source grid, MT%q_trans(Evolve_q%npoints+1:) (camb/cmbmain.f90:597-623) */
+  int WantTransfer, transfer_num_redshifts;
+  double tautf[GALCAMB_MAX_TRANSFER_Z];
+  int nk_transfer;
+  const double* k_transfer;
+  double H0;                                              /* CP%H0 (Transfer_kh = k/(H0/100)) */
 } galcamb_model;
 
 /* --- context --------------------------------------------------------------------------------------- */
@@ -121,6 +130,13 @@ int galcamb_get_transfers_(const int* slot, double* Delta_p_l_k);
 int galcamb_get_cls_(const int* slot, double* iCl, double* Cl); /* either pointer may be NULL */
 int galcamb_put_cls_(const int* slot, const double* Cl);         /* feed stage 5 with host-computed Cl_scalar */
 int galcamb_get_status_(const int* slot, int* status);           /* per-slot CAMB error id */
+/* Matter transfer functions of a slot after galcamb_evolve_sources_ (models with WantTransfer): MT%num_q_trans,
+ * the number of redshifts, MT%q_trans, MT%TransferData as FP64 in Fortran order TransferData(13, num_q_trans, nz)
+ * = C [nz][num_q_trans][13] (camb/modules.f90:1896-1915; rows 2..13 already divided by k^2 like outtransf,
+ * camb/equations_galileon.f90:2093) and sigma_8 per redshift (Transfer_Get_sigmas, camb/modules.f90:2450).  Any
+ * pointer may be NULL.  Replaces the transfer taps of camb/cmbmain.f90:1017-1068 and TransferOut (:1151-1201). */
+int galcamb_get_transfer_(const int* slot, int* num_q_trans, int* num_redshifts, double* q_trans, double* TransferData,
+                          double* sigma8);
 
 /* stage 5 (post-step of the path): lens_Cls -> CorrFuncFullSky -> CorrFuncFullSkyImpl, camb/lensing.f90:78-528
  * (lensing_method = 1, AccurateBB = F, no tensors), on the device-resident Cl_scalar of every slot of the batch.
@@ -168,6 +184,11 @@ typedef struct galcamb_params {
   int DoLensing, AccuratePolarization, AccurateReionization, MassiveNuMethod, DoLateRadTruncation, HighAccuracyDefault;
   double AccuracyBoost, lSampleBoost, lAccuracyBoost;
   int use_spline_template;
+  /* CP%WantTransfer + TransferParams (camb/modules.f90:75-90): kmax in 1/Mpc, redshifts in descending order;
+   * transfer_high_precision = T is not restated (error_unsupported_params) */
+  int WantTransfer, transfer_high_precision, transfer_k_per_logint, transfer_num_redshifts;
+  double transfer_kmax;
+  double transfer_redshifts[GALCAMB_MAX_TRANSFER_Z];
 } galcamb_params;
 
 void galcamb_default_params_(galcamb_params* p);
@@ -216,6 +237,9 @@ int galcamb_multi_single_cls_(const int* ngpu, const galcamb_params* params, dou
  * algorithmic work counters of SURVEY.md section 8(d). */
 int galcamb_get_timings_(double* ms /*[8]: evolve, spline_k, los, cls, lensing, -, bessel, total of 0..3*/);
 int galcamb_get_counters_(double* c /*[4]: n_derivs, sum_n, n_out, n_iter*/);
+/* wall clock [ms] of the host-side phases of the last galcamb_batch_cls_ call: packing, H2D enqueue, upload as a whole,
+   device stages 1-4, D2H of the C_l, collection of the pre-staged models, -, - */
+int galcamb_get_host_timings_(double* ms /*[8]*/);
 /* K1 executes fewer RHS evaluations than the reference algorithm counts in n_derivs: the y' of an output time
  * (camb/equations_galileon.f90:1297) is the k1 of the next step.  s[0] = evaluations executed, s[1] = outputs served so. */
 int galcamb_get_evolve_stats_(double* s /*[2]*/);

@@ -82,6 +82,13 @@ constexpr int nrhopn = 2000;    // camb/modules.f90:1554
 constexpr int nqmax0 = 80;
 constexpr int max_l_evolve = 256;  // camb/equations_galileon.f90:192
 constexpr int GAL_NB = 29999;      // camb/galileon.cc:72
+constexpr int max_transfer_redshifts = 150;  // camb/modules.f90:64
+// camb/modules.f90:1876-1884 (rows of TransferData)
+enum {
+  Transfer_kh = 1, Transfer_cdm, Transfer_b, Transfer_g, Transfer_r, Transfer_nu, Transfer_tot, Transfer_nonu,
+  Transfer_tot_de, Transfer_Weyl, Transfer_Newt_vel_cdm, Transfer_Newt_vel_baryon, Transfer_vel_baryon_cdm,
+  Transfer_max = Transfer_vel_baryon_cdm
+};
 
 // error ids, camb/constants.f90:70-79
 enum {
@@ -171,6 +178,13 @@ struct Params {
   float lAccuracyBoost = 1.f;
   int use_spline_template = 1;
   int nthreads = 0;  // 0: OpenMP default
+  // matter transfer functions (TransferParams, camb/modules.f90:75-90); kmax in 1/Mpc, redshifts descending
+  int WantTransfer = 0;
+  int transfer_high_precision = 0;  // only F is restated
+  double transfer_kmax = 0.9;
+  int transfer_k_per_logint = 0;
+  int transfer_num_redshifts = 1;
+  double transfer_redshifts[max_transfer_redshifts] = {0};
 };
 
 // ---------------------------------------------------------------- model state
@@ -270,6 +284,12 @@ struct Model {
   std::string error_msg;
   Counters cnt;
   std::vector<double> per_k_trials;  // per source-k trial-step counts (for load-balance studies)
+  // MatterTransferData (camb/modules.f90:1896-1915); TransferData kept in FP64 (the reference stores default real)
+  std::vector<double> tautf;         // 1-based, camb/cmbmain.f90:783-793
+  int num_q_trans = 0;
+  std::vector<double> q_trans;       // 1-based: Evolve_q points, then the transfer-only wavenumbers
+  std::vector<double> TransferData;  // (Transfer_max, num_q_trans, nz): idx = (e-1) + Transfer_max*((ik-1) + num_q_trans*(iz-1))
+  std::vector<double> sigma_8;       // per transfer redshift
 };
 
 inline void GlobalError(Model& M, const char* msg, int id) {
@@ -324,6 +344,9 @@ void initlval(Model& M, int max_l);
 void cmb_InitVars(Model& M);
 void SetkValuesForSources(Model& M);
 void CalcAllSources(Model& M);            // hot loop 1
+void InitTransfer(Model& M);              // camb/cmbmain.f90:508-632
+void TransferOut(Model& M);               // camb/cmbmain.f90:1151-1201
+void Transfer_Get_sigmas(Model& M);       // camb/modules.f90:2304-2370, :2450-2472 (R = 8/h Mpc, total matter)
 void InitSourceInterpolation(Model& M);
 void GenerateBessels(Model& M);
 void bjl(int L, double X, double& JL);

@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE (oracle) -- plain C API over the C++ oracle for ctypes (tests/, smoke(),
 // bench.py cpu_baseline / --impl reference only).  See orc.hpp header.
+#include <algorithm>
 #include <map>
 
 #include "orc.hpp"
@@ -30,6 +31,7 @@ int orc_set(void* h, const char* name, double v) {
   D(RECFAST_fudge) D(RECFAST_fudge_He) I(RECFAST_Heswitch) I(RECFAST_Hswitch)
   I(Max_l) D(Max_eta_k) I(DoLensing) I(AccuratePolarization) I(AccurateReionization) I(MassiveNuMethod)
   I(DoLateRadTruncation) I(HighAccuracyDefault) D(AccuracyBoost) D(lSampleBoost) I(use_spline_template) I(nthreads)
+  I(WantTransfer) I(transfer_high_precision) D(transfer_kmax) I(transfer_k_per_logint) I(transfer_num_redshifts)
 #undef D
 #undef I
   if (n == "lAccuracyBoost") { P.lAccuracyBoost = (float)v; return 0; }
@@ -42,6 +44,41 @@ int orc_set(void* h, const char* name, double v) {
     if (b == "Nu_mass_degeneracies") { P.Nu_mass_degeneracies[i] = v; return 0; }
   }
   return 1;
+}
+
+// transfer redshifts, descending like CP%Transfer%redshifts (camb/modules.f90:2538-2570)
+int orc_set_transfer_redshifts(void* h, const double* z, int n) {
+  Params& P = ((Model*)h)->P;
+  if (n < 0 || n > max_transfer_redshifts) return 1;
+  P.transfer_num_redshifts = n;
+  for (int i = 0; i < n; i++) P.transfer_redshifts[i] = z[i];
+  return 0;
+}
+// matter-transfer results: dims = {Transfer_max, num_q_trans, nz}; any pointer may be NULL
+int orc_get_transfer(void* h, int* dims, double* TransferData, double* q_trans, double* tautf, double* sigma8) {
+  Model& M = *(Model*)h;
+  const int nz = M.P.WantTransfer ? M.P.transfer_num_redshifts : 0;
+  if (dims) {
+    dims[0] = Transfer_max;
+    dims[1] = M.num_q_trans;
+    dims[2] = nz;
+  }
+  if (TransferData) std::copy(M.TransferData.begin(), M.TransferData.end(), TransferData);
+  if (q_trans)
+    for (int i = 1; i <= M.num_q_trans; i++) q_trans[i - 1] = M.q_trans[i];
+  if (tautf)
+    for (int i = 1; i <= nz; i++) tautf[i - 1] = M.tautf[i];
+  if (sigma8)
+    for (int i = 0; i < nz && i < (int)M.sigma_8.size(); i++) sigma8[i] = M.sigma_8[i];
+  return 0;
+}
+int orc_stage_transfer(void* h) {  // TransferOut + Transfer_Get_sigmas (after orc_stage_sources)
+  Model& M = *(Model*)h;
+  if (!M.P.WantTransfer) return 0;
+  TransferOut(M);
+  if (M.error_flag) return M.error_flag;
+  Transfer_Get_sigmas(M);
+  return 0;
 }
 
 // "physical" convenience of camb/inidriver.F90:107-118 (use_physical = T, omk = 0)
@@ -77,6 +114,7 @@ int orc_stage_initvars(void* h) {
   cmb_InitVars(M);
   if (M.error_flag) return M.error_flag;
   SetkValuesForSources(M);
+  if (M.P.WantTransfer) InitTransfer(M);
   M.SourceNum = M.WantLateTime ? 3 : 2;
   M.C_last = M.WantLateTime ? 6 : 3;
   return 0;

@@ -16,6 +16,7 @@ namespace orc {
 static inline long nint(double x) { return std::lround(x); }
 
 void CalcScalarSourcesForK(Model& M, int q_ix, Counters& cnt, int& err, std::string& errmsg);
+void GetTransferForK(Model& M, int q_ix, Counters& cnt, int& err, std::string& errmsg);
 double orc_GetTauStart(const Model& M, double q);
 
 static const double xlimmin = 35.0, xlimfrac = 0.05;  // camb/bessels.f90:14
@@ -113,11 +114,146 @@ void cmb_InitVars(Model& M) {
   M.dtaurec = M.dtaurec_q;
   M.max_etak_scalar = initAccuracyBoost * std::fmax(1700.0, M.maximum_qeta) / 20;
   if (M.maximum_qeta < 3500 && P.AccuracyBoost < 2) M.max_etak_scalar = M.max_etak_scalar * 1.5;
-  const double maxq = M.qmax;
+  double maxq = M.qmax;  // WantCls (:757-762)
+  if (P.WantTransfer) maxq = std::fmax(M.qmax, P.transfer_kmax);
   const double taumin = orc_GetTauStart(M, maxq);
   inithermo(M, taumin, M.tau0);
   if (M.error_flag) return;
   GaugeInterface_Init(M);
+  // times of the transfer-function outputs, :783-793  (TimeOfz, camb/modules.f90:574-580)
+  M.tautf.assign(1, 0.0);
+  if (P.WantTransfer) {
+    for (int itf = 1; itf <= P.transfer_num_redshifts; itf++) {
+      M.tautf.push_back(std::fmin(DeltaTime(M, 0.0, 1.0 / (P.transfer_redshifts[itf - 1] + 1.0)), M.tau0));
+      if (itf > 1 && M.tautf[itf] <= M.tautf[itf - 1]) {
+        GlobalError(M, "Transfer redshifts not set or out of order", error_unsupported_params);
+        return;
+      }
+    }
+  }
+}
+
+// camb/cmbmain.f90:508-632 (flat, WantCls): the transfer wavenumber grid, merged behind the C_l source grid
+void InitTransfer(Model& M) {
+  const Params& P = M.P;
+  std::vector<double> q_transfer(1, 0.0);  // 1-based
+  int num_q_trans = 0;
+  if (P.transfer_k_per_logint == 0) {
+    double boost = P.AccuracyBoost;
+    if (P.transfer_high_precision) boost = boost * 1.5;
+    const double q_switch_lowk1 = SP(0.7) / M.taurst;
+    const double dlog_lowk1 = 2 * boost;
+    const double q_switch_lowk = 8 / M.taurst;
+    double dlog_lowk = 8 * boost;
+    if (P.HighAccuracyDefault) dlog_lowk = dlog_lowk * 2.5;
+    const double q_switch_osc = std::fmin(P.transfer_kmax, 30 / M.taurst);
+    double d_osc = 200 * boost;
+    if (P.HighAccuracyDefault) d_osc = d_osc * SP(1.8);
+    double q_switch_highk = std::fmin(P.transfer_kmax, 60 / M.taurst);
+    const double dlog_osc = 17 * boost;
+    if (P.HighAccuracyDefault) q_switch_highk = std::fmin(P.transfer_kmax, 90 / M.taurst);
+    const double dlog_highk = 3 * boost;
+    const double amin = 5e-5;
+    int nq = (int)((std::log(P.transfer_kmax / amin)) * d_osc) + 1;
+    q_transfer.assign(nq + 2, 0.0);
+    nq = (int)((std::log(q_switch_lowk1 / amin)) * dlog_lowk1) + 1;
+    for (int q_ix = 1; q_ix <= nq; q_ix++) q_transfer[q_ix] = amin * std::exp((q_ix - 1) / dlog_lowk1);
+    num_q_trans = nq;
+    nq = (int)(std::log(q_switch_lowk / q_transfer[num_q_trans]) * dlog_lowk) + 1;
+    for (int q_ix = 1; q_ix <= nq; q_ix++) q_transfer[num_q_trans + q_ix] = q_transfer[num_q_trans] * std::exp(q_ix / dlog_lowk);
+    num_q_trans = num_q_trans + nq;
+    nq = (int)((q_switch_osc - q_transfer[num_q_trans]) * d_osc) + 1;
+    for (int q_ix = 1; q_ix <= nq; q_ix++) q_transfer[num_q_trans + q_ix] = q_transfer[num_q_trans] + q_ix / d_osc;
+    num_q_trans = num_q_trans + nq;
+    if (P.transfer_kmax > q_transfer[num_q_trans]) {
+      nq = (int)(std::log(q_switch_highk / q_transfer[num_q_trans]) * dlog_osc) + 1;
+      for (int q_ix = 1; q_ix <= nq; q_ix++) q_transfer[num_q_trans + q_ix] = q_transfer[num_q_trans] * std::exp(q_ix / dlog_osc);
+      num_q_trans = num_q_trans + nq;
+    }
+    if (P.transfer_kmax > q_transfer[num_q_trans]) {
+      nq = (int)(std::log(P.transfer_kmax / q_transfer[num_q_trans]) * dlog_highk) + 1;
+      for (int q_ix = 1; q_ix <= nq; q_ix++) q_transfer[num_q_trans + q_ix] = q_transfer[num_q_trans] * std::exp(q_ix / dlog_highk);
+      num_q_trans = num_q_trans + nq;
+    }
+  } else {
+    num_q_trans = (int)((std::log(P.transfer_kmax) - std::log(M.qmin)) * P.transfer_k_per_logint) + 1;
+    q_transfer.assign(num_q_trans + 1, 0.0);
+    for (int q_ix = 1; q_ix <= num_q_trans; q_ix++) q_transfer[q_ix] = M.qmin * (double)std::exp((float)q_ix / (float)P.transfer_k_per_logint);  // default-real exp
+  }
+  // WantCls: keep the source grid, append the transfer wavenumbers above its top (:597-623)
+  const int ntodo = num_q_trans, nk = M.Evolve_q.npoints;
+  int first_i = ntodo + 1;
+  for (int q_ix = 1; q_ix <= ntodo; q_ix++)
+    if (q_transfer[q_ix] > M.Evolve_q.Highest + 1e-4) {
+      first_i = q_ix;
+      break;
+    }
+  M.num_q_trans = first_i > ntodo ? nk : nk + (ntodo - first_i + 1);
+  M.q_trans.assign(M.num_q_trans + 1, 0.0);
+  for (int i = 1; i <= nk; i++) M.q_trans[i] = M.Evolve_q.points[i];
+  for (int i = nk + 1; i <= M.num_q_trans; i++) M.q_trans[i] = q_transfer[first_i + (i - nk - 1)];
+  M.TransferData.assign((size_t)Transfer_max * M.num_q_trans * P.transfer_num_redshifts, 0.0);
+  M.sigma_8.assign(P.transfer_num_redshifts, 0.0);
+}
+
+// camb/cmbmain.f90:1151-1179: the wavenumbers beyond the C_l source grid (OpenMP over k like the reference)
+void TransferOut(Model& M) {
+  const int nk = M.Evolve_q.npoints;
+  const int nth = M.P.nthreads > 0 ? M.P.nthreads : omp_get_max_threads();
+  int err_any = 0;
+  std::string err_msg;
+  Counters total;
+#pragma omp parallel for schedule(dynamic) num_threads(nth)
+  for (int q_ix = nk + 1; q_ix <= M.num_q_trans; q_ix++) {
+    Counters c;
+    int err = 0;
+    std::string msg;
+    GetTransferForK(M, q_ix, c, err, msg);
+#pragma omp critical
+    {
+      total.n_derivs += c.n_derivs;
+      total.sum_n_trial += c.sum_n_trial;
+      total.flop_ode += c.flop_ode;
+      if (err) {
+        err_any = err;
+        err_msg = msg;
+      }
+    }
+  }
+  M.cnt.n_derivs += total.n_derivs;
+  M.cnt.sum_n_trial += total.sum_n_trial / 8.0;
+  M.cnt.flop_ode += total.flop_ode;
+  if (err_any) GlobalError(M, err_msg.c_str(), err_any);
+}
+
+// Transfer_Get_sigmas -> Transfer_Get_SigmaR, camb/modules.f90:2450-2472, :2304-2370: sigma_8 of the total matter
+// transfer function (transfer_power_var = Transfer_tot, R = 8 Mpc/h) at every transfer redshift
+void Transfer_Get_sigmas(Model& M) {
+  const int nz = M.P.transfer_num_redshifts;
+  const double radius = 8.0, H = M.P.H0 / 100.0;
+  std::vector<double> dsig8(nz, 0.0), dsig8o(nz, 0.0), sig8(nz, 0.0);
+  double lnko = 0, dlnk;
+  for (int ik = 1; ik <= M.num_q_trans; ik++) {
+    const double kh = M.TransferData[(Transfer_kh - 1) + (size_t)Transfer_max * (ik - 1)];
+    if (kh == 0) continue;
+    const double k = kh * H;
+    const double x = kh * radius;
+    const double win = 3 * (std::sin(x) - x * std::cos(x)) / (x * x * x);
+    const double lnk = std::log(k);
+    if (ik == 1)
+      dlnk = 0.5;
+    else
+      dlnk = lnk - lnko;
+    const double powers = ScalarPower(M, k);
+    for (int iz = 0; iz < nz; iz++) {
+      const double t = M.TransferData[(Transfer_tot - 1) + (size_t)Transfer_max * ((ik - 1) + (size_t)M.num_q_trans * iz)];
+      dsig8[iz] = ((win * (k * k)) * (win * (k * k))) * powers * (t * t);
+      sig8[iz] = sig8[iz] + (dsig8[iz] + dsig8o[iz]) * dlnk / 2;
+      dsig8o[iz] = dsig8[iz];
+    }
+    lnko = lnk;
+  }
+  for (int iz = 0; iz < nz; iz++) M.sigma_8[iz] = std::sqrt(sig8[iz]);
 }
 
 // camb/cmbmain.f90:797-852
@@ -653,6 +789,7 @@ int run_model(Model& M, double* stage_times, bool reuse_bessels) {
   if (M.error_flag) return M.error_flag;
   tn = now_s(); st[1] = tn - t; t = tn;
   SetkValuesForSources(M);
+  if (M.P.WantTransfer) InitTransfer(M);
   if (M.WantLateTime) {
     M.SourceNum = 3;
     M.C_last = 6;
@@ -662,6 +799,11 @@ int run_model(Model& M, double* stage_times, bool reuse_bessels) {
   }
   CalcAllSources(M);
   if (M.error_flag) return M.error_flag;
+  if (M.P.WantTransfer) {  // camb/cmbmain.f90:217-237
+    TransferOut(M);
+    if (M.error_flag) return M.error_flag;
+    Transfer_Get_sigmas(M);
+  }
   tn = now_s(); st[2] = tn - t; t = tn;
   InitSourceInterpolation(M);
   tn = now_s(); st[3] = tn - t; t = tn;

@@ -33,6 +33,8 @@ struct EvolutionVars {
   int lmaxnu_tau[max_nu + 1] = {0};
   bool nu_nonrelativistic[max_nu + 1] = {false};
   double denlk[max_l_evolve + 1], denlk2[max_l_evolve + 1], polfack[max_l_evolve + 1], Kf[max_l_evolve + 1];
+  bool TransferOnly = false;         // camb/equations_galileon.f90:209
+  double* OutputTransfer = nullptr;  // 1-based row of TransferData while outtransf runs (:264)
   // oracle bookkeeping
   const Model* M = nullptr;
   Counters* cnt = nullptr;
@@ -265,6 +267,10 @@ static void GetNumEqns(EvolutionVars& EV) {
       EV.lmaxgpol = EV.lmaxgpol * 2;
     }
   }
+  if (EV.TransferOnly) {  // :872-875
+    EV.lmaxgpol = std::min(EV.lmaxgpol, (int)nint(5 * lAB));
+    EV.lmaxg = std::min(EV.lmaxg, (int)nint(6 * lAB));
+  }
   EV.poltruncfac = (double)EV.lmaxgpol / std::max(1, (EV.lmaxgpol - 2));
   EV.MaxlNeeded = std::max(std::max(EV.lmaxg, EV.lmaxnr), std::max(EV.lmaxgpol, EV.lmaxnu));
   if (EV.MaxlNeeded > max_l_evolve) {
@@ -434,6 +440,31 @@ static void MassiveNuVarsOut(const EvolutionVars& EV, const double* y, const dou
   dgrho = dgrho + dgrhonu;
 }
 
+// MassiveNuVarsOut as called from the transfer tap of derivs (camb/equations_galileon.f90:2335: only clxnu_all and
+// dgpi present; the pinudot work of :1033-1037 feeds no requested output and is left out)
+static void MassiveNuVarsOut_transfer(const EvolutionVars& EV, const double* y, double a, double& clxnu_all, double& dgpi) {
+  const Model& M = *EV.M;
+  double grhonu = 0, dgrhonu = 0;
+  for (int nu_i = 1; nu_i <= M.Nu_mass_eigenstates; nu_i++) {
+    const double grhormass_t = M.grhormass[nu_i] / (a * a);
+    double rhonu, pnu, clxnu, qnu, pinu, dpnu;
+    Nu_background(M, a * M.nu_masses[nu_i], rhonu, pnu);
+    if (EV.MassiveNuApprox[nu_i]) {
+      clxnu = y[EV.nu_ix[nu_i]];
+      pinu = y[EV.nu_ix[nu_i] + 3];
+    } else {
+      Nu_Integrate_L012(EV, y, a, nu_i, clxnu, qnu, &dpnu, &pinu);
+      clxnu = clxnu / rhonu;
+      pinu = pinu / rhonu;
+    }
+    const double grhonu_t = grhormass_t * rhonu;
+    grhonu = grhonu + grhonu_t;
+    dgrhonu = dgrhonu + grhonu_t * clxnu;
+    dgpi = dgpi + grhonu_t * pinu;
+  }
+  clxnu_all = dgrhonu / grhonu;
+}
+
 // camb/equations_galileon.f90:2098-2589.  ay, ayprime 1-based.  EV%pig / EV%pigdot are written
 // as a side effect during tight coupling (SURVEY.md section 9 trap 1).
 static void derivs(EvolutionVars& EV, int n, double tau, const double* ay, double* ayprime) {
@@ -538,6 +569,29 @@ static void derivs(EvolutionVars& EV, int n, double tau, const double* ay, doubl
   z = (0.5 * dgrho / k + etak) / adotoa;
   const double sigma = (z + 1.5 * dgq / k2);
   ayprime[2] = 0.5 * dgq;
+  if (EV.OutputTransfer) {  // :2325-2353 (pig is not yet assigned during tight coupling in the reference: 0 here)
+    double* T = EV.OutputTransfer;
+    T[Transfer_kh] = k / (M.P.H0 / 100.0);
+    T[Transfer_cdm] = clxc;
+    T[Transfer_b] = clxb;
+    T[Transfer_g] = clxg;
+    T[Transfer_r] = clxr;
+    double clxnu_all = 0;
+    double dgpi = grhor_t * pir + grhog_t * pig;
+    if (M.Num_Nu_massive != 0) MassiveNuVarsOut_transfer(EV, ay, a, clxnu_all, dgpi);
+    if (gal) {
+      const double dgpigal_t = gal_Pigal(M, a, hub, xgal, dh, dx, dgrho, dgq, dgpi, etak, dphi, k);
+      dgpi = dgpi + dgpigal_t;
+    }
+    T[Transfer_nu] = clxnu_all;
+    T[Transfer_tot] = dgrho_matter / grho_matter;
+    T[Transfer_nonu] = (grhob_t * clxb + grhoc_t * clxc) / (grhob_t + grhoc_t);
+    T[Transfer_tot_de] = dgrho / grho_matter;
+    T[Transfer_Weyl] = -(dgrho + 3 * dgq * adotoa / k) / (1.0 * 2) - dgpi / 2;
+    T[Transfer_Newt_vel_cdm] = -k * sigma / adotoa;
+    T[Transfer_Newt_vel_baryon] = -k * (vb + sigma) / adotoa;
+    T[Transfer_vel_baryon_cdm] = vb;
+  }
   const double clxcdot = -k * z;
   ayprime[3] = clxcdot;
   const double clxbdot = -k * (z + vb);
@@ -1114,9 +1168,22 @@ static double GetTauStart(const Model& M, double q) {
 }
 double orc_GetTauStart(const Model& M, double q) { return GetTauStart(M, q); }
 
+// camb/equations_galileon.f90:2078-2095: one derivs call with the transfer tap armed; rows 2..Transfer_max / k^2.
+// Arr = 1-based row of Transfer_max entries.
+static void outtransf(EvolutionVars& EV, const double* y, double tau, double* Arr, std::vector<double>& yprime_buf) {
+  double* yprime = yprime_buf.data();
+  for (int i = 0; i <= EV.nvar; i++) yprime[i] = 0;
+  EV.k2_buf = EV.q2;  // flat (:2066-2067 of the vector twin; derivs sets the same buffers)
+  EV.OutputTransfer = Arr;
+  derivs(EV, EV.ScalEqsToPropagate, tau, y, yprime);
+  EV.OutputTransfer = nullptr;
+  for (int e = Transfer_kh + 1; e <= Transfer_max; e++) Arr[e] = Arr[e] / EV.k2_buf;
+}
+
 // DoSourcek + CalcScalarSources, camb/cmbmain.f90:662-689, :917-1071.
-// Writes Src(q_ix, 1:S, 1:nt) into M.Src.  Thread-safe across distinct q_ix; errors and
-// counters are returned per call and merged by the caller.
+// Writes Src(q_ix, 1:S, 1:nt) into M.Src (and, with WantTransfer, TransferData(:, q_ix, :) at the transfer redshifts,
+// :1017-1030, :1049-1068).  Thread-safe across distinct q_ix; errors and counters are returned per call and merged
+// by the caller.
 void CalcScalarSourcesForK(Model& M, int q_ix, Counters& cnt, int& err, std::string& errmsg) {
   EvolutionVars EV;
   EV.M = &M;
@@ -1131,20 +1198,37 @@ void CalcScalarSourcesForK(Model& M, int q_ix, Counters& cnt, int& err, std::str
   double c[25];
   for (int i = 0; i < 25; i++) c[i] = 0;
   double sources[4];
-  Model Merr_stub;  // not used for state; errors recorded through a light-weight proxy below
-  (void)Merr_stub;
   initial(EV, y.data(), taustart);
   double tau = taustart;
   int ind = 1;
-  const double tol1 = base_tol / std::exp(M.P.AccuracyBoost - 1);
+  double tol1 = base_tol / std::exp(M.P.AccuracyBoost - 1);
   // local error sink (GlobalError writes into a Model); use a tiny Model-like proxy
   struct ErrSink : Model {};
   static thread_local ErrSink* sink = nullptr;
   if (!sink) sink = new ErrSink();
   sink->error_flag = 0;
+  const bool WantTransfer = M.P.WantTransfer != 0;
+  const int ntf = WantTransfer ? M.P.transfer_num_redshifts : 0;
+  const double* tautf = M.tautf.data();  // 1-based
+  auto trow = [&](int itf) { return M.TransferData.data() + (size_t)Transfer_max * ((q_ix - 1) + (size_t)M.num_q_trans * (itf - 1)) - 1; };
+  int itf = 1;
+  if (WantTransfer) {
+    if (M.P.transfer_high_precision) tol1 = tol1 / 100;
+    while (itf <= ntf && M.TimeSteps.points[2] > tautf[itf]) {  // :1022-1029
+      GaugeInterface_EvolveScal(EV, tau, y.data(), tautf[itf], tol1, ind, c, w.data(), *sink, ybuf);
+      if (sink->error_flag) {
+        err = sink->error_flag;
+        errmsg = sink->error_msg;
+        return;
+      }
+      outtransf(EV, y.data(), tau, trow(itf), yprime);
+      itf = itf + 1;
+    }
+  }
   for (int j = 2; j <= nt; j++) {
     const double tauend = M.TimeSteps.points[j];
-    if ((EV.q * tauend > M.max_etak_scalar && tauend > M.taurend) && !M.WantLateTime) {
+    if ((EV.q * tauend > M.max_etak_scalar && tauend > M.taurend) && !M.WantLateTime &&
+        (!WantTransfer || tau > tautf[ntf])) {
       for (int s = 1; s <= S; s++) M.Src[(q_ix - 1) + (size_t)nk * ((s - 1) + (size_t)S * (j - 1))] = 0;
     } else {
       GaugeInterface_EvolveScal(EV, tau, y.data(), tauend, tol1, ind, c, w.data(), *sink, ybuf);
@@ -1155,7 +1239,65 @@ void CalcScalarSourcesForK(Model& M, int q_ix, Counters& cnt, int& err, std::str
       }
       output(EV, y.data(), j, tau, sources, S, yprime);
       for (int s = 1; s <= S; s++) M.Src[(q_ix - 1) + (size_t)nk * ((s - 1) + (size_t)S * (j - 1))] = sources[s];
+      // transfer functions, :1049-1068 (the `goto 101` loop)
+      while (WantTransfer && itf <= ntf) {
+        if (j < nt) {
+          if (tauend < tautf[itf] && M.TimeSteps.points[j + 1] > tautf[itf]) {
+            GaugeInterface_EvolveScal(EV, tau, y.data(), tautf[itf], tol1, ind, c, w.data(), *sink, ybuf);
+            if (sink->error_flag) {
+              err = sink->error_flag;
+              errmsg = sink->error_msg;
+              return;
+            }
+          }
+        }
+        bool again = false;
+        if (std::fabs(tau - tautf[itf]) < 1.e-5) {
+          outtransf(EV, y.data(), tau, trow(itf), yprime);
+          itf = itf + 1;
+          if (j < nt)
+            if (itf <= ntf && M.TimeSteps.points[j + 1] > tautf[itf]) again = true;
+        }
+        if (!again) break;
+      }
     }
+  }
+  err = 0;
+}
+
+// One iteration of TransferOut's loop + GetTransfer, camb/cmbmain.f90:1164-1177, :1181-1201: a wavenumber beyond the
+// C_l source grid, evolved through the transfer redshifts only.
+void GetTransferForK(Model& M, int q_ix, Counters& cnt, int& err, std::string& errmsg) {
+  EvolutionVars EV;
+  EV.M = &M;
+  EV.cnt = &cnt;
+  EV.TransferOnly = true;
+  EV.q = M.q_trans[q_ix];
+  EV.q2 = EV.q * EV.q;
+  EV.q_ix = q_ix;
+  double tau = GetTauStart(M, EV.q);
+  GetNumEqns(EV);
+  const int nvar = EV.nvar;
+  std::vector<double> w((size_t)nvar * 9, 0.0), y(nvar + 2, 0.0), ybuf(nvar + 2, 0.0), yprime(nvar + 2, 0.0);
+  double c[25];
+  for (int i = 0; i < 25; i++) c[i] = 0;
+  double atol = base_tol / std::exp(M.P.AccuracyBoost - 1);
+  if (M.P.transfer_high_precision) atol = atol / 10000;
+  int ind = 1;
+  initial(EV, y.data(), tau);
+  struct ErrSink : Model {};
+  static thread_local ErrSink* sink = nullptr;
+  if (!sink) sink = new ErrSink();
+  sink->error_flag = 0;
+  for (int i = 1; i <= M.P.transfer_num_redshifts; i++) {
+    GaugeInterface_EvolveScal(EV, tau, y.data(), M.tautf[i], atol, ind, c, w.data(), *sink, ybuf);
+    if (sink->error_flag) {
+      err = sink->error_flag;
+      errmsg = sink->error_msg;
+      return;
+    }
+    outtransf(EV, y.data(), tau, M.TransferData.data() + (size_t)Transfer_max * ((q_ix - 1) + (size_t)M.num_q_trans * (i - 1)) - 1,
+              yprime);
   }
   err = 0;
 }

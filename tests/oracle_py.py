@@ -57,9 +57,11 @@ def lib():
         L.orc_set_physical.argtypes = [C.c_void_p] + [C.c_double] * 4
         L.orc_load_template.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_run.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
-        for s in ("background", "initvars", "sources", "spline_k", "bessels", "los", "cls", "lensing", "qgrid"):
+        for s in ("background", "initvars", "sources", "spline_k", "bessels", "los", "cls", "lensing", "qgrid", "transfer"):
             getattr(L, "orc_stage_" + s).argtypes = [C.c_void_p]
         L.orc_alloc_sources.argtypes = [C.c_void_p]
+        L.orc_set_transfer_redshifts.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_get_transfer.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.orc_source_k.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         L.orc_error.argtypes = [C.c_void_p]
         L.orc_error.restype = C.c_char_p
@@ -181,3 +183,20 @@ class Oracle:
 
     def iCl(self):
         return self.arr("iCl").reshape(self.geti("C_last"), self.geti("nl"))
+
+    # matter transfer functions (camb/cmbmain.f90:508-632, :1151-1201; camb/modules.f90:1876-1915)
+    def want_transfer(self, redshifts=(0.0,), kmax=0.9, k_per_logint=0):
+        """Transfer outputs at the given redshifts (descending, like CP%Transfer%redshifts); kmax in 1/Mpc."""
+        z = np.ascontiguousarray(redshifts, dtype=np.float64)
+        if self.L.orc_set_transfer_redshifts(self.h, z.ctypes.data, len(z)):
+            raise ValueError("too many transfer redshifts")
+        self.set(WantTransfer=1, transfer_kmax=kmax, transfer_k_per_logint=k_per_logint)
+
+    def transfer(self):
+        """dict: TransferData [nz][nq][13] (= Fortran TransferData(13, nq, nz), FP64), q_trans, tautf, sigma8."""
+        dims = (C.c_int * 3)()
+        self.L.orc_get_transfer(self.h, dims, None, None, None, None)
+        ne, nq, nz = list(dims)
+        T, q, t, s8 = np.zeros((nz, nq, ne)), np.zeros(nq), np.zeros(nz), np.zeros(nz)
+        self.L.orc_get_transfer(self.h, dims, T.ctypes.data, q.ctypes.data, t.ctypes.data, s8.ctypes.data)
+        return dict(TransferData=T, q_trans=q, tautf=t, sigma8=s8)

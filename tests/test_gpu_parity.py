@@ -471,6 +471,67 @@ def test_exact_step_history_without_fma_contraction():
         assert float(m.group(1)) == 2 * n_oracle, (knob, r.stdout)
 
 
+# Matter transfer functions.  Rows of TransferData that are reproducible: the matter rows (cdm, b, tot,
+# nonu, baryon-cdm velocity) and k/h; the photon / massless-neutrino / total-with-dark-energy / Weyl rows of the
+# wavenumbers BEYOND the source grid carry the Galileon field perturbation, which at k ~ 1/Mpc is integrated in long free
+# steps and is sensitive to last-bit differences (two CPU builds of the oracle, -ffp-contract=off vs -march=native,
+# differ there by 2e-3 ... 8e-3 of the element, 1e-5 of the row's maximum over k; LCDM has no such rows).
+MATTER_ROWS = [0, 1, 2, 6, 7, 12]
+
+
+def _transfer_errors(T, To):
+    a, b = T["TransferData"], To["TransferData"]
+    assert a.shape == b.shape
+    elem = float(np.max(np.abs(a[:, :, MATTER_ROWS] / b[:, :, MATTER_ROWS] - 1)))
+    den = np.max(np.abs(b), axis=1, keepdims=True)
+    den[den == 0] = 1.0
+    return elem, float(np.max(np.abs(a - b) / den))
+
+
+@pytest.mark.parametrize("P", [LCDM, GAL], ids=["lcdm", "galileon"])
+def test_matter_transfer_against_oracle(gpu, P):
+    """CP%WantTransfer through the product: transfer times and extra wavenumbers from the pre-stage, outtransf taps inside
+    the time-step loop of K1 (camb/cmbmain.f90:1017-1068), the transfer-only wavenumbers (TransferOut, :1151-1201) and
+    sigma_8 (camb/modules.f90:2304-2370), against the oracle; the C_l of the same call too."""
+    from oracle_py import Oracle
+    from cosmomc_galileon_b200 import make_params, prestage
+    Z, kmax, lmax = (2.0, 0.5, 0.0), 1.0, 800
+    o = Oracle(lmax=lmax, **P)
+    o.want_transfer(redshifts=Z, kmax=kmax)
+    o.run()
+    To = o.transfer()
+    p = make_params(Max_l=lmax, Max_eta_k=2.0 * lmax, WantTransfer=1, transfer_kmax=kmax, transfer_num_redshifts=len(Z),
+                    transfer_redshifts=Z, **P)
+    tabs, st = prestage([p])
+    assert st == [0]
+    run_gpu(gpu, tabs[0])
+    T = gpu.transfer(0)
+    assert T["q_trans"].size > o.geti("nk") and np.array_equal(T["q_trans"], To["q_trans"])
+    elem, rowmax = _transfer_errors(T, To)
+    assert elem < TOL_TRANSFER, elem                                 # per element, matter rows
+    assert rowmax < (TOL_TRANSFER if not P.get("use_galileon") else 2e-5), rowmax  # every row, relative to its maximum over k
+    assert np.max(np.abs(T["sigma8"] / To["sigma8"] - 1)) < 1e-9
+    assert colmax(gpu.Src(), o.Src()) < TOL_TRANSFER
+    assert np.max(np.abs(gpu.Cls()[1] / o.Cl() - 1)) < TOL_CL
+    assert abs(gpu.counters()["n_derivs"] / o.get("n_derivs") - 1) < 1e-4
+
+
+def test_matter_transfer_through_the_batch_kernel():
+    """The same through the lane-per-item form of K1 (forced with GALCAMB_OCTET_ITEMS=0 in a fresh process)."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GALCAMB_OCTET_ITEMS="0")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_transfer_probe.py"), "3"], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"transfer err (\S+) sigma8 err (\S+) q_trans err (\S+) Src err (\S+) Cl err (\S+)", r.stdout)
+    assert m, r.stdout
+    te, s8, qe, se, ce = (float(x) for x in m.groups())
+    assert te < 2e-5 and s8 < 1e-9 and qe == 0 and se < TOL_TRANSFER and ce < TOL_CL, r.stdout
+
+
 def test_massless_neutrino_model(gpu):
     """No massive eigenstate (omnuh2 = 0 -> Num_Nu_massive = 0, camb/modules.f90:307-316): the neutrino blocks of the
     state vector and the table lookups disappear."""

@@ -93,6 +93,58 @@ def test_lensed_lcdm_against_reference_theory_cl():
         assert 0.85 < cl[2, l - 2] / r[4] < 1.0
 
 
+REF_MIN = "/root/reference/data/base_plikHM_TT_lowTEB.minimum"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MIN), reason="reference tree not mounted")
+def test_sigma8_against_reference_minimum():
+    """The matter-transfer path (transfer taps of CalcScalarSources, TransferOut, Transfer_Get_sigmas:
+    camb/cmbmain.f90:508-632, :1017-1068, :1151-1201, camb/modules.f90:2304-2370) pinned on numbers the reference tree
+    holds: the derived sigma8 and sigma8(z=0.57) of its Planck best-fit file, computed by CosmoMC with get_sigma8 from
+    exactly these transfer functions.  Same caveat as the theory_cl pin (other CAMB vintage / accuracy settings): 2e-3."""
+    want = {}
+    for line in open(REF_MIN):
+        f = line.split()
+        if len(f) >= 3 and f[2] in ("sigma8", "sigma8z057"):
+            want[f[2]] = float(f[1])
+    assert set(want) == {"sigma8", "sigma8z057"}
+    o = Oracle(ombh2=0.02224017, omch2=0.1192851, omnuh2=0.000645, H0=67.44385, optical_depth=0.07602569,
+               ScalarPowerAmp=float(np.exp(3.081122) * 1e-10), an=0.9633217, YHe=0.245341, delta_redshift=0.5,
+               DoLensing=1, lmax=2650, DoLateRadTruncation=0)
+    o.want_transfer(redshifts=(0.57, 0.0), kmax=0.8)  # CosmoMC: kmax = max(0.8, power_kmax), source/Calculator_CAMB.f90:834
+    o.run()
+    T = o.transfer()
+    assert T["q_trans"].size > o.geti("nk")  # wavenumbers beyond the source grid took the GetTransfer path
+    assert abs(T["sigma8"][1] / want["sigma8"] - 1) < 2e-3, (T["sigma8"], want)
+    assert abs(T["sigma8"][0] / want["sigma8z057"] - 1) < 2e-3, (T["sigma8"], want)
+    # with transfer outputs the high-k modes are evolved past k*tau = max_etak_scalar instead of being zeroed
+    # (camb/cmbmain.f90:1034-1036) and the thermo table starts earlier (maxq, :757-762): the C_l move at the 1e-3 level
+    o2 = Oracle(ombh2=0.02224017, omch2=0.1192851, omnuh2=0.000645, H0=67.44385, optical_depth=0.07602569,
+                ScalarPowerAmp=float(np.exp(3.081122) * 1e-10), an=0.9633217, YHe=0.245341, delta_redshift=0.5,
+                DoLensing=1, lmax=2650, DoLateRadTruncation=0)
+    o2.run()
+    assert 1e-6 < np.max(np.abs(o.Cl()[0] / o2.Cl()[0] - 1)) < 3e-3
+
+
+def test_transfer_taps_properties():
+    """Transfer rows against what they must be by construction: Transfer_kh = k/h on the merged wavenumber list, the
+    baryon+CDM row is the density-weighted mean of the b and cdm rows, and a wavenumber beyond the source grid
+    (TransferOnly) continues the rows of the source grid smoothly."""
+    P = dict(ombh2=0.0226, omch2=0.112, omnuh2=0.00064, H0=70.0)
+    o = Oracle(lmax=400, template=False, **P)
+    o.want_transfer(redshifts=(1.0, 0.0), kmax=0.5)
+    o.run()
+    T = o.transfer()
+    D, q, nk = T["TransferData"], T["q_trans"], o.geti("nk")
+    assert D.shape == (2, q.size, 13) and q.size > nk and np.all(np.diff(q) > 0)
+    assert np.max(np.abs(D[:, :, 0] / (q / 0.70) - 1)) < 1e-14
+    ob, oc = 0.0226, 0.112
+    assert np.max(np.abs((ob * D[:, :, 2] + oc * D[:, :, 1]) / (ob + oc) / D[:, :, 7] - 1)) < 1e-12
+    lt = np.log(np.abs(D[1, :, 6]))
+    assert abs((lt[nk] - lt[nk - 1]) - (lt[nk - 1] - lt[nk - 2]) * np.log(q[nk] / q[nk - 1]) / np.log(q[nk - 1] / q[nk - 2])) < 0.05
+    assert np.all(T["sigma8"] > 0) and T["sigma8"][1] > T["sigma8"][0]  # growth
+
+
 def test_lensing_golden_and_properties():
     z = np.load(os.path.join(GOLD, "config3_lensing_golden.npz"))
     P = json.loads(bytes(z["params_json"]).decode())

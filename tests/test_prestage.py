@@ -92,3 +92,34 @@ def test_prestage_batch_is_threaded_and_rejects_bad_points():
     single, _ = prestage([good], nthreads=1)
     for n in ("cs2", "dotmu", "vis", "k", "q", "gal_h"):
         assert np.array_equal(tabs[0].d[n], single[0].d[n]) and np.array_equal(tabs[3].d[n], single[0].d[n]), n
+
+
+def test_transfer_grids_against_oracle():
+    """CP%WantTransfer in the product pre-stage: the transfer times tautf (camb/cmbmain.f90:783-793), the wavenumbers
+    InitTransfer appends beyond the source grid (:508-632) and the earlier thermo-table start (maxq, :757-762)
+    are identical to the oracle's."""
+    from oracle_py import Oracle
+    from cosmomc_galileon_b200 import make_params, prestage
+    GAL = dict(ombh2=0.0221743, omch2=0.1177806, omnuh2=0.00064, H0=78.07227, use_galileon=1, c2=-8.438179, c3=-3.366555,
+               c4=-1.03411, cG=0.001188243)
+    Z = (2.0, 0.5, 0.0)
+    for kmax, kpl in ((1.0, 0), (0.6, 5)):
+        o = Oracle(lmax=800, **GAL)
+        o.want_transfer(redshifts=Z, kmax=kmax, k_per_logint=kpl)
+        o.stage("background", "initvars")
+        To = o.transfer()
+        p = make_params(Max_l=800, Max_eta_k=1600.0, WantTransfer=1, transfer_kmax=kmax, transfer_k_per_logint=kpl,
+                        transfer_num_redshifts=len(Z), transfer_redshifts=Z, **GAL)
+        tabs, st = prestage([p], nthreads=1)
+        assert st == [0]
+        t = tabs[0].d
+        nk = o.geti("nk")
+        assert t["nk"] == nk and t["WantTransfer"] == 1 and t["H0"] == GAL["H0"]
+        assert t["nk_transfer"] == To["q_trans"].size - nk > 0
+        assert np.max(np.abs(t["k_transfer"] / To["q_trans"][nk:] - 1)) < 1e-14
+        assert np.max(np.abs(t["tautf"] / To["tautf"] - 1)) < 1e-12
+        assert t["tauminn"] == o.get("tauminn")
+    # out-of-order redshifts and the unsupported high-precision mode are rejected with error_unsupported_params
+    bad = make_params(Max_l=800, Max_eta_k=1600.0, WantTransfer=1, transfer_num_redshifts=2, transfer_redshifts=(0.0, 1.0), **GAL)
+    hp = make_params(Max_l=800, Max_eta_k=1600.0, WantTransfer=1, transfer_high_precision=1, **GAL)
+    assert prestage([bad, hp], nthreads=1)[1] == [5, 5]
