@@ -19,7 +19,10 @@ VARIANT = os.environ.get("GALCAMB_VARIANT", "")
 OBJ = os.path.join(HERE, "_build" + ("_" + VARIANT if VARIANT else ""))
 LIB = os.path.join(HERE, "libgalcamb_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 SOURCES = ["evolve.cu", "evolve_batch.cu", "los.cu", "lensing.cu", "capi.cu", "fp64_peak.cu", "galileon_host.cu", "prestage.cu"]
-TRANSFER_SOURCES = ["evolve.cu", "evolve_batch.cu"]  # also built with -DGC_WITH_TRANSFER (CP%WantTransfer)
+# the two K1 files are also built with -DGC_WITH_TRANSFER (CP%WantTransfer taps); the lane-per-item one also with
+# -DGC_EV_NU=1 (records sized for one massive-neutrino eigenstate: +5 % on a 1024-point batch; the eight-lane kernel
+# measured 4-10 % slower built that way and keeps the general records)
+TRANSFER_SOURCES = ["evolve.cu", "evolve_batch.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FMAD = os.environ.get("GALCAMB_FMAD", "true")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=" + FMAD, "-std=c++17", "-Xcompiler",
@@ -42,6 +45,7 @@ def build(verbose=False, force=False):
     # (source, object, extra flags): the two K1 files are compiled a second time with the matter-transfer taps
     units = [(s, s.replace(".cu", ".o"), []) for s in SOURCES]
     units += [(s, s.replace(".cu", "_tr.o"), ["-DGC_WITH_TRANSFER"]) for s in TRANSFER_SOURCES]
+    units += [("evolve_batch.cu", "evolve_batch_nu1.o", ["-DGC_EV_NU=1"])]
     for s, o, extra in units:
         src, obj = os.path.join(CSRC, s), os.path.join(OBJ, o)
         if force or _stale(obj, [src] + headers):

@@ -52,7 +52,7 @@ class CModel(C.Structure):
         + [(n, _D) for n in "ScalarPowerAmp an n_run n_runrun k_0_scalar".split()]
         + [("lmax", _I)]
         + [("WantTransfer", _I), ("transfer_num_redshifts", _I), ("tautf", _D * MAX_TRANSFER_Z), ("nk_transfer", _I),
-           ("k_transfer", _P), ("H0", _D)]
+           ("k_transfer", _P), ("H0", _D), ("ALens", _D), ("ALens_Fiducial", _D)]
     )
 
 
@@ -73,7 +73,7 @@ class CParams(C.Structure):
         + [(n, _D) for n in "AccuracyBoost lSampleBoost lAccuracyBoost".split()]
         + [("use_spline_template", _I)]
         + [(n, _I) for n in "WantTransfer transfer_high_precision transfer_k_per_logint transfer_num_redshifts".split()]
-        + [("transfer_kmax", _D), ("transfer_redshifts", _D * MAX_TRANSFER_Z)]
+        + [("transfer_kmax", _D), ("transfer_redshifts", _D * MAX_TRANSFER_Z), ("ALens", _D), ("ALens_Fiducial", _D)]
     )
 
 
@@ -153,7 +153,7 @@ class ModelTables:
         m = CModel()
         d = self.d
         for n in SCALARS:
-            if n in ("WantTransfer", "transfer_num_redshifts", "nk_transfer", "H0"):  # absent from older fixtures
+            if n in ("WantTransfer", "transfer_num_redshifts", "nk_transfer", "H0", "ALens", "ALens_Fiducial"):  # absent from older fixtures
                 setattr(m, n, d.get(n, 0))
             elif n != "n_tau_regions":
                 setattr(m, n, d[n])
@@ -382,6 +382,12 @@ class GalCamb:
                                                  C.byref(_D(n_run)), C.byref(_D(n_runrun)), C.byref(_D(k_0_scalar))))
         d = self.models[slot].d
         d["ScalarPowerAmp"], d["an"], d["n_run"], d["n_runrun"], d["k_0_scalar"] = ScalarPowerAmp, an, n_run, n_runrun, k_0_scalar
+
+    def set_alens(self, slot, ALens=1.0, ALens_Fiducial=0.0):
+        """CAMBmain's ALens and lensing's ALens_Fiducial for a resident slot (source/Calculator_CAMB.f90:130-131)."""
+        self._chk(self.L.galcamb_set_alens_(C.byref(_I(slot)), C.byref(_D(ALens)), C.byref(_D(ALens_Fiducial))))
+        d = self.models[slot].d
+        d["ALens"], d["ALens_Fiducial"] = ALens, ALens_Fiducial
 
     def TransfersToPowers(self, do_lensing=False):
         rc = self.L.galcamb_transfers_to_powers_(C.byref(_I(int(do_lensing))))

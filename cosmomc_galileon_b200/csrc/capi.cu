@@ -33,6 +33,10 @@ extern "C" cudaError_t gc_launch_evolve_tr(const DevModel*, const int2*, int, in
 extern "C" int gc_evolve_warps_per_cta_tr(int);
 extern "C" void gc_upload_constants_batch_tr();
 extern "C" cudaError_t gc_launch_evolve_batch_tr(const DevModel*, const int2*, int, double*, int, int*, unsigned long long*, cudaStream_t);
+// ... and the lane-per-item kernel with its lane records sized for one massive-neutrino eigenstate (-DGC_EV_NU=1): used
+// when no model of the batch has more
+extern "C" void gc_upload_constants_batch_nu1();
+extern "C" cudaError_t gc_launch_evolve_batch_nu1(const DevModel*, const int2*, int, double*, int, int*, unsigned long long*, cudaStream_t);
 extern "C" cudaError_t gc_set_bess_regions(const GcRegions*);
 extern "C" cudaError_t gc_launch_bessels(double2*, const double*, const int*, double*, int, int, cudaStream_t);
 extern "C" cudaError_t gc_launch_spline_k(const DevModel*, int, int, cudaStream_t);
@@ -264,6 +268,7 @@ int galcamb_init_(const int* device) {
   gc_upload_constants_batch();
   gc_upload_constants_tr();
   gc_upload_constants_batch_tr();
+  gc_upload_constants_batch_nu1();
   CK(cudaMalloc((void**)&g.d_counters, 24 * sizeof(unsigned long long)));
   CK(cudaMalloc((void**)&g.d_queue, sizeof(unsigned)));
   CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, g.device));
@@ -496,6 +501,9 @@ static int pack_model(int islot, const galcamb_model* m) {
   D.nk_tr = m->WantTransfer ? m->nk_transfer : 0;
   for (int i = 0; i < GC_MAX_TF; i++) D.tautf[i] = i < D.ntf ? m->tautf[i] : 0.0;
   D.h0_100 = m->H0 / 100.0;
+  if (m->ALens < 0 || m->ALens_Fiducial < 0) return fail(5, "negative lensing amplitude");
+  D.ALens = m->ALens > 0 ? m->ALens : 1.0;  // a zero-filled struct means the default
+  D.ALens_fid = m->ALens_Fiducial;
   D.TimeSteps.count = m->n_tau_regions;
   D.TimeSteps.npoints = m->nt;
   D.TimeSteps.Lowest = m->tau[0];
@@ -673,6 +681,8 @@ int galcamb_evolve_sources_(void) {
   const int NVP = NV;
   bool want_tr = false;
   for (auto& s : g.slots) want_tr = want_tr || s.host.WantTransfer != 0;
+  bool want_nu1 = !want_tr && !getenv("GALCAMB_NO_NU1");  // (experiment knob: always the general kernels)
+  for (auto& s : g.slots) want_nu1 = want_nu1 && s.host.n_eig <= 1;
   const int warps_per_sm = want_tr ? gc_evolve_warps_per_cta_tr(NVP) : gc_evolve_warps_per_cta(NVP);
   const bool batch_form = total_items > octet_items || warps_per_sm < 1;
   g.k1_form = batch_form ? 1 : 0;
@@ -772,8 +782,8 @@ int galcamb_evolve_sources_(void) {
   }
   CK(cudaEventRecord(g.ev[0], g.stream));
   if (batch_form) {
-    CK((want_tr ? gc_launch_evolve_batch_tr : gc_launch_evolve_batch)(g.d_models, g.d_items, nitems, g.d_ws, NV, g.d_status,
-                                                                        g.d_counters, g.stream));
+    CK((want_tr ? gc_launch_evolve_batch_tr : want_nu1 ? gc_launch_evolve_batch_nu1 : gc_launch_evolve_batch)(
+        g.d_models, g.d_items, nitems, g.d_ws, NV, g.d_status, g.d_counters, g.stream));
   } else {
     CK((want_tr ? gc_launch_evolve_tr : gc_launch_evolve)(g.d_models, g.d_items, ngroups, NVP, g.num_sms, g.d_queue, g.d_status,
                                                             g.d_counters, g.stream));
@@ -979,6 +989,14 @@ int galcamb_set_primordial_(const int* slot, const double* ScalarPowerAmp, const
   D.n_run = *n_run;
   D.n_runrun = *n_runrun;
   D.k_0_scalar = *k_0_scalar;
+  return 0;
+}
+
+int galcamb_set_alens_(const int* slot, const double* ALens, const double* ALens_Fiducial) {
+  if (*slot < 0 || *slot >= (int)g.slots.size() || !g.slots[*slot].set) return fail(5, "bad slot");
+  if (!(*ALens > 0) || *ALens_Fiducial < 0) return fail(5, "bad lensing amplitude");
+  g.slots[*slot].host.ALens = *ALens;
+  g.slots[*slot].host.ALens_fid = *ALens_Fiducial;
   return 0;
 }
 

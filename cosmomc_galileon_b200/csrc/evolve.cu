@@ -35,9 +35,12 @@
 // (camb/cmbmain.f90:1017-1068, :1151-1201) in the control flow, in its own namespace and under entry-point names ending
 // in _tr: the default kernels stay exactly as they are without the taps (the extra state-machine phases cost registers
 // in the hot loop: +14 % on a 1024-point batch when compiled in unconditionally).
-#ifdef GC_WITH_TRANSFER
+#if defined(GC_WITH_TRANSFER)
 #define gc gc_tr
 #define GC_ENTRY(name) name##_tr
+#elif defined(GC_EV_NU)
+#define gc gc_nu1
+#define GC_ENTRY(name) name##_nu1
 #else
 #define GC_ENTRY(name) name
 #endif
@@ -100,8 +103,8 @@ struct Item {
   int win_i0;
   double galwin[GC_OCT * 6];  // eight consecutive rows of the Galileon background spline (+ 1/(a_{i+1} - a_i)), per trial step
   // massive-neutrino velocity factors of the current stage: v = q/E and E/q per (eigenstate, momentum node)
-  double vv[GC_MAX_NU * GC_MAX_NQ], ivv[GC_MAX_NU * GC_MAX_NQ];
-  double nub[3 * GC_MAX_NU];  // rhonu, pnu, w = pnu/rhonu of the current stage per eigenstate (dynamic-index copy of BG)
+  double vv[GC_EV_NU * GC_MAX_NQ], ivv[GC_EV_NU * GC_MAX_NQ];
+  double nub[3 * GC_EV_NU];  // rhonu, pnu, w = pnu/rhonu of the current stage per eigenstate (dynamic-index copy of BG)
   // work counters: n_derivs / sum_n count what the reference algorithm evaluates
   unsigned n_derivs, sum_n, n_out, n_shared, n_exec, n_trial;
 };
@@ -237,7 +240,7 @@ __device__ __forceinline__ double adotoa_at(const DevModel& M, bool gal, double 
     grhoa2 = grhoa2 + M.grhov * (a2 * a2);
     if (M.Num_Nu_massive != 0) {
 #pragma unroll
-      for (int nu_i = 0; nu_i < GC_MAX_NU; nu_i++)
+      for (int nu_i = 0; nu_i < GC_EV_NU; nu_i++)
         if (nu_i < M.n_eig) {
           const double2 rp = nu_background_ni(&M, a * M.nu_masses[nu_i]);
           rhonu[nu_i] = rp.x;
@@ -258,7 +261,7 @@ struct BG {
   double grhob_t, grhoc_t, grhor_t, grhog_t, gpres;
   double photbar, pb43;
   double iop, ipb;  // tight coupling: 1/opacity, 1/(1 + pb43)
-  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
+  double rhonu[GC_EV_NU], pnu[GC_EV_NU];
   double chi_p, chi_d, chi_g, chi_e, q_d, q_p, q_g;  // Chigal, qgal as linear forms (galileon_fast.cuh)
   GalPhi2Lin D;                                       // dphisecond
   GalPiLin P;                                         // Pigal (tight coupling only)
@@ -280,7 +283,7 @@ __device__ __forceinline__ void bg_eval(const DevModel& M, const EV& e, bool tig
   b.pb43 = 4.0 / 3 * b.photbar;
   if (!have_nu) {
 #pragma unroll
-    for (int i = 0; i < GC_MAX_NU; i++)
+    for (int i = 0; i < GC_EV_NU; i++)
       if (i < M.n_eig) {
         const double2 rp = nu_background_ni(&M, a * M.nu_masses[i]);
         b.rhonu[i] = rp.x;
@@ -292,7 +295,7 @@ __device__ __forceinline__ void bg_eval(const DevModel& M, const EV& e, bool tig
   if (gal) {
     double lam_nu = 0;
 #pragma unroll
-    for (int i = 0; i < GC_MAX_NU; i++)
+    for (int i = 0; i < GC_EV_NU; i++)
       if (i < M.n_eig) lam_nu += M.grhormass[i] * b.pnu[i];
     const GalConst GC{M.c2, M.c3, M.c4, M.c5, M.cG, M.h0, M.orad};
     GalFast F;
@@ -327,7 +330,7 @@ __device__ __forceinline__ void bg_eval(const DevModel& M, const EV& e, bool tig
     gpres = gpres + grhov_t * (-1.0);
   if (M.Num_Nu_massive > 0) {
 #pragma unroll
-    for (int i = 0; i < GC_MAX_NU; i++)
+    for (int i = 0; i < GC_EV_NU; i++)
       if (i < M.n_eig) gpres = gpres + (M.grhormass[i] * ia2) * b.pnu[i];
   }
   b.gpres = gpres;
@@ -419,13 +422,13 @@ __device__ __forceinline__ void rhs_scalar(const DevModel* __restrict__ Mp, EV* 
   double dgq = grhob_t * vb;
   if (M.Num_Nu_massive > 0) {  // MassiveNuVars, :1209-1252
 #pragma unroll
-    for (int i = 0; i < GC_MAX_NU; i++) {  // BG lives in registers: a copy the rolled loops below can index
+    for (int i = 0; i < GC_EV_NU; i++) {  // BG lives in registers: a copy the rolled loops below can index
       nub[i] = b.rhonu[i];
-      nub[GC_MAX_NU + i] = b.pnu[i];
+      nub[GC_EV_NU + i] = b.pnu[i];
     }
 #pragma unroll 1
     for (int nu_i = 0; nu_i < M.n_eig; nu_i++) {
-      const double rhonu = nub[nu_i], pnu = nub[GC_MAX_NU + nu_i];
+      const double rhonu = nub[nu_i], pnu = nub[GC_EV_NU + nu_i];
       const double grhormass_t = M.grhormass[nu_i] * ia2;
       const double irho = 1.0 / rhonu;
       double clxnu, qnu;
@@ -440,7 +443,7 @@ __device__ __forceinline__ void rhs_scalar(const DevModel* __restrict__ Mp, EV* 
       const double grhonu_t = grhormass_t * rhonu;
       dgrho_matter = dgrho_matter + grhonu_t * clxnu;
       dgq = dgq + grhonu_t * qnu;
-      nub[2 * GC_MAX_NU + nu_i] = pnu * irho;
+      nub[2 * GC_EV_NU + nu_i] = pnu * irho;
     }
   }
   const double adotoa = b.adotoa;
@@ -575,7 +578,7 @@ __device__ __forceinline__ void rhs_scalar(const DevModel* __restrict__ Mp, EV* 
       const double G11_t = e.G11[nu_i] * ia3;
       const double G30_t = e.G30[nu_i] * ia3;
       const int o = e.nu_ix[nu_i];
-      const double w = nub[2 * GC_MAX_NU + nu_i];
+      const double w = nub[2 * GC_EV_NU + nu_i];
       AT(ayp, o) = -k * z * (w + 1) + 3 * adotoa * (w * AT(ay, o) - AT(ay, o + 1)) - k * AT(ay, o + 2);
       AT(ayp, o + 1) = (3 * w - 2) * adotoa * AT(ay, o + 1) - 5.0 / 3 * k * z * w - k / 3 * G11_t;
       AT(ayp, o + 2) = (3 * w - 1) * adotoa * AT(ay, o + 2) - k * (2.0 / 3 * 1.0 * AT(ay, o + 3) - AT(ay, o + 1));
@@ -1103,7 +1106,7 @@ __device__ __noinline__ void init_item(const ItemMem m, const DevModel* models, 
 #endif
   L.e.pig = 0;
   L.e.pigdot = 0;
-  for (int i = 0; i < GC_MAX_NU; i++) {
+  for (int i = 0; i < GC_EV_NU; i++) {
     L.e.nu_ix[i] = 0;
     L.e.nq[i] = 0;
     L.e.lmaxnu_tau[i] = 0;
@@ -1216,7 +1219,7 @@ __device__ __forceinline__ void warp_step(const ItemMem& m, const LTab& T, int s
         case 6: as = row_val<5>(y1, temp, ka); break;
         default: as = row_val<6>(y1, temp, ka); break;
       }
-      double hb = 0, xg = 0, rn[GC_MAX_NU] = {0}, pn[GC_MAX_NU] = {0};
+      double hb = 0, xg = 0, rn[GC_EV_NU] = {0}, pn[GC_EV_NU] = {0};
       const double ad = adotoa_at(M, gal, as, L.galwin, win_i0, hb, xg, rn, pn);
       const double kav = ad * as;
       switch (s) {
@@ -1236,7 +1239,7 @@ __device__ __forceinline__ void warp_step(const ItemMem& m, const LTab& T, int s
         hbar_own = hb;
         xgal_own = xg;
 #pragma unroll
-        for (int i = 0; i < GC_MAX_NU; i++) {
+        for (int i = 0; i < GC_EV_NU; i++) {
           b.rhonu[i] = rn[i];
           b.pnu[i] = pn[i];
         }

@@ -19,9 +19,14 @@
 // (camb/cmbmain.f90:1017-1068, :1151-1201) in the control flow, in its own namespace and under entry-point names ending
 // in _tr: the default kernels stay exactly as they are without the taps (the extra state-machine phases cost registers
 // in the hot loop: +14 % on a 1024-point batch when compiled in unconditionally).
-#ifdef GC_WITH_TRANSFER
+// -DGC_EV_NU=1 compiles it a third time with the per-item records sized for one massive-neutrino eigenstate (entry points
+// ending in _nu1): the launcher's choice when no model of the batch has more (the usual CosmoMC set-up).
+#if defined(GC_WITH_TRANSFER)
 #define gc gc_tr
 #define GC_ENTRY(name) name##_tr
+#elif defined(GC_EV_NU)
+#define gc gc_nu1
+#define GC_ENTRY(name) name##_nu1
 #else
 #define GC_ENTRY(name) name
 #endif
@@ -80,7 +85,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
   }
   const double grhob_t = M.grhob * ia, grhoc_t = M.grhoc * ia, grhor_t = M.grhornomass * ia2, grhog_t = M.grhog * ia2;
   // massive-neutrino background at this a (shared by MassiveNuVars, GetdHdX and dtauda)
-  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
+  double rhonu[GC_EV_NU], pnu[GC_EV_NU];
   for (int i = 0; i < M.n_eig; i++) Nu_background(M, a * M.nu_masses[i], rhonu[i], pnu[i]);
   double grhov_t = 0, xgal = 0, grhogal_t = 0, hbar = 0;
   GalFast F;
@@ -105,7 +110,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
   double grho_matter = grhob_t + grhoc_t;
   double dgrho_matter = grhob_t * clxb + grhoc_t * clxc;
   double dgq = grhob_t * vb;
-  double wnu_arr[GC_MAX_NU];
+  double wnu_arr[GC_EV_NU];
   if (M.Num_Nu_massive > 0) {  // MassiveNuVars, :1209-1252
     for (int nu_i = 0; nu_i < M.n_eig; nu_i++) {
       const double grhormass_t = M.grhormass[nu_i] * ia2;
@@ -1279,7 +1284,7 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
 #endif
     L.e.pig = 0;
     L.e.pigdot = 0;
-    for (int i = 0; i < GC_MAX_NU; i++) {
+    for (int i = 0; i < GC_EV_NU; i++) {
       L.e.nu_ix[i] = 0;
       L.e.nq[i] = 0;
       L.e.lmaxnu_tau[i] = 0;

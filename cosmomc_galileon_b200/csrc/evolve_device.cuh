@@ -33,20 +33,27 @@ namespace gc {
 // float-rounded literals of the reference's default-real constants (no _dl suffix)
 #define GC_SP(x) ((double)(x##f))
 
+// eigenstates the per-item records are sized for: GC_MAX_NU (= the reference's max_nu) in the general kernels, 1 in the
+// -DGC_EV_NU=1 compilation the launcher picks when no model of the batch has more than one mass eigenstate (smaller
+// records: the lane-per-item kernel then leaves 60 KB instead of 28 KB of each SM to the L1 cache)
+#ifndef GC_EV_NU
+#define GC_EV_NU GC_MAX_NU
+#endif
+
 struct EV {
   double q, k, k2, ik, ik2;  // ik = 1/k, ik2 = 1/k^2 (per-lane constants)
   // 16/8-bit layout fields: the record sits in shared memory once per work item (csrc/evolve.cu) or per lane
   // (csrc/evolve_batch.cu: 256 records per SM)
   short w_ix, r_ix, g_ix, polind, nu_pert_ix, nvar, neq;
   short lmaxg, lmaxnr, lmaxnu, lmaxgpol, lmaxnu_pert;
-  short nu_ix[GC_MAX_NU];
-  unsigned char nq[GC_MAX_NU], lmaxnu_tau[GC_MAX_NU];
+  short nu_ix[GC_EV_NU];
+  unsigned char nq[GC_EV_NU], lmaxnu_tau[GC_EV_NU];
   bool TightCoupling, high_ktau, no_nu, no_phot, has_nu_rel;
 #ifdef GC_WITH_TRANSFER
   bool TransferOnly;  // a wavenumber beyond the source grid, camb/cmbmain.f90:1165
 #endif
-  bool MassiveNuApprox[GC_MAX_NU], nu_nonrel[GC_MAX_NU];
-  double G11[GC_MAX_NU], G30[GC_MAX_NU], MassiveNuApproxTime[GC_MAX_NU];
+  bool MassiveNuApprox[GC_EV_NU], nu_nonrel[GC_EV_NU];
+  double G11[GC_EV_NU], G30[GC_EV_NU], MassiveNuApproxTime[GC_EV_NU];
   double TightSwitchoffTime, pig, pigdot, poltruncfac;
 };
 
@@ -436,7 +443,7 @@ __device__ inline void GetNumEqns(const DevModel& M, EV& e) {
   e.TightCoupling = true;
   e.no_phot = false;
   e.no_nu = false;
-  for (int i = 0; i < GC_MAX_NU; i++) e.MassiveNuApprox[i] = false;
+  for (int i = 0; i < GC_EV_NU; i++) e.MassiveNuApprox[i] = false;
   if (M.HighAccuracyDefault && M.AccuratePolarization)
     e.lmaxg = max((int)nintd(11 * lAB), 3);
   else
@@ -586,7 +593,7 @@ static __device__ __noinline__ void output_sources(const DevModel* __restrict__ 
   const double grhov_t = M.grhov * pow(a, 2.0);
   double grho = grhob_t + grhoc_t + grhor_t + grhog_t;
   double gpres = (grhog_t + grhor_t) / 3;
-  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
+  double rhonu[GC_EV_NU], pnu[GC_EV_NU];
   for (int i = 0; i < M.n_eig; i++) Nu_background(M, a * M.nu_masses[i], rhonu[i], pnu[i]);
   double xgal = 0, hub = 0, hbar = 0;
   GalFast F;
@@ -790,7 +797,7 @@ static __device__ __noinline__ void transfer_outputs(const DevModel* __restrict_
     dphiprime = AT(y, e.w_ix + 1);
   }
   const double grhob_t = M.grhob / a, grhoc_t = M.grhoc / a, grhor_t = M.grhornomass / a2, grhog_t = M.grhog / a2;
-  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
+  double rhonu[GC_EV_NU], pnu[GC_EV_NU];
   for (int i = 0; i < M.n_eig; i++) Nu_background(M, a * M.nu_masses[i], rhonu[i], pnu[i]);
   double xgal = 0, hbar = 0;
   GalFast F;

@@ -36,8 +36,8 @@ __global__ void lens_ltab_kernel(double4* __restrict__ ta, double4* __restrict__
   tb[l] = make_double4(lr, l > 1 ? 0.244949 / sqrt(3.0 * lf - 8.0) : 0.0, sqrt((double)l), 0.0);
 }
 
-// Cphil3, CTT, CEE, CTE (:221-253) as cin[m][l] = (Cphil3, CTT, CEE, CTE); status[m] = 1 if the spectrum is not
-// realistically normalised (:230-235)
+// Cphil3, CTT, CEE, CTE (:221-257) as cin[m][l] = (Cphil3, CTT, CEE, CTE); status[m] (zeroed by the launcher) is set
+// if the spectrum (:230-235) or the high-L template (:243-249) is not realistically normalised
 __global__ void lens_prep_kernel(const DevModel* __restrict__ models, LensGeom G, const double* __restrict__ tmpl,
                                  const double* __restrict__ tmpl_pp, int lmax_tmpl, double4* __restrict__ cin,
                                  int* __restrict__ status) {
@@ -57,7 +57,7 @@ __global__ void lens_prep_kernel(const DevModel* __restrict__ models, LensGeom G
     };
     if (l <= G.Max_l) {
       out = row(l);
-      if (l == 10) status[m] = out.x > (double)1e-7f ? 1 : 0;
+      if (l == 10 && out.x > (double)1e-7f) atomicOr(&status[m], 1);
     } else {
       const int nT = lmax_tmpl - 1;
       const int L = G.Max_l;
@@ -68,6 +68,11 @@ __global__ void lens_prep_kernel(const DevModel* __restrict__ models, LensGeom G
       sc = (2 * l + 1) / (4 * pi) * 2 * pi / (l * (l + 1));
       out = make_double4(tmpl_pp[l - 2] * fac * sc, tmpl[l - 2] * fac2 * sc, tmpl[(size_t)nT + l - 2] * fac2 * sc,
                          tmpl[2 * (size_t)nT + l - 2] * fac2 * sc);
+      if (l == G.Max_l + 1 && out.x > (double)1e-7f) atomicOr(&status[m], 1);  // :243-249
+    }
+    if (M.ALens_fid > 0) {  // :252-257: the lensing potential of the template itself, scaled
+      const double sc = (2 * l + 1) / (4 * pi) * 2 * pi / (l * (l + 1));
+      out.x = sc * tmpl_pp[l - 2] * M.ALens_fid;
     }
   }
   cin[(size_t)m * (G.lmax + 1) + l] = out;
@@ -290,6 +295,7 @@ extern "C" cudaError_t gc_launch_lensing(const DevModel* models, int nmodels, co
   G.apod_w3 = geom[5];
   G.nblk = geom[6];
   G.dtheta = dtheta;
+  cudaMemsetAsync(status, 0, (size_t)nmodels * sizeof(int), st);
   gc::lens_prep_kernel<<<dim3((G.lmax + 256) / 256, nmodels), 256, 0, st>>>(models, G, tmpl, tmpl_pp, lmax_tmpl, cin, status);
   gc::lens_corr_kernel<<<dim3(G.nblk, nmodels), gc::LENS_THREADS, 0, st>>>(G, ta, tb, cin, apod, partial);
   gc::lens_finish_kernel<<<dim3((G.lmax_lensed - 1 + 127) / 128, nmodels), 128, 0, st>>>(models, G, partial, status, lensed);

@@ -390,9 +390,9 @@ __global__ void __launch_bounds__(256) cl_kernel(const DevModel* __restrict__ mo
     M.iCl[1 * nl + j] = red[1][0] * dbletmp * ctnorm;
     M.iCl[2 * nl + j] = red[2][0] * dbletmp * sqrt(ctnorm);
     if (S > 2) {
-      M.iCl[3 * nl + j] = red[3][0] * fourpi * (ell * ell * ell * ell);
-      M.iCl[4 * nl + j] = red[4][0] * fourpi * (ell * ell * ell);
-      M.iCl[5 * nl + j] = red[5][0] * fourpi * (ell * ell * ell) * sqrt(ctnorm);
+      M.iCl[3 * nl + j] = M.ALens * red[3][0] * fourpi * (ell * ell * ell * ell);  // camb/cmbmain.f90:2254-2259
+      M.iCl[4 * nl + j] = sqrt(M.ALens) * red[4][0] * fourpi * (ell * ell * ell);
+      M.iCl[5 * nl + j] = sqrt(M.ALens) * red[5][0] * fourpi * (ell * ell * ell) * sqrt(ctnorm);
     }
   }
 }

@@ -82,4 +82,7 @@ struct DevModel {
   double h0_100;                 // CP%h0/100 (Transfer_kh = k/h)
   const double* k_tr;            // [nk_tr]
   double* Transfer;              // [ntf][nk + nk_tr][13] FP64  (== Fortran TransferData(13, num_q_trans, nz))
+  // lensing amplitude knobs CosmoMC sets before every call (source/Calculator_CAMB.f90:130-131)
+  double ALens;      // camb/cmbmain.f90:122, :2254-2259
+  double ALens_fid;  // ALens_Fiducial, camb/lensing.f90:52, :252-257 (0 = off)
 };

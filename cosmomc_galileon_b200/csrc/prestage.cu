@@ -1361,6 +1361,8 @@ static void fill_view(const Model& M, galcamb_model* m) {
   m->nk_transfer = (int)M.k_transfer.size();
   m->k_transfer = M.k_transfer.empty() ? nullptr : M.k_transfer.data();
   m->H0 = P.H0;
+  m->ALens = P.ALens > 0 ? P.ALens : 1.0;
+  m->ALens_Fiducial = P.ALens_Fiducial;
 }
 
 }  // namespace pre
@@ -1379,6 +1381,7 @@ void galcamb_default_params_(galcamb_params* p) {
   p->DoLateRadTruncation = 1; p->HighAccuracyDefault = 1; p->AccuracyBoost = 1; p->lSampleBoost = 1; p->lAccuracyBoost = 1;
   p->use_spline_template = 1;
   p->WantTransfer = 0; p->transfer_kmax = 0.9; p->transfer_num_redshifts = 1; p->transfer_redshifts[0] = 0;
+  p->ALens = 1; p->ALens_Fiducial = 0;
 }
 
 int galcamb_sizeof_params_(void) { return (int)sizeof(galcamb_params); }

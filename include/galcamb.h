@@ -92,6 +92,10 @@ typedef struct galcamb_model {
   int nk_transfer;
   const double* k_transfer;
   double H0;                                              /* CP%H0 (Transfer_kh = k/(H0/100)) */
+  /* lensing amplitudes CosmoMC sets before every call (source/Calculator_CAMB.f90:130-131): ALens scales C_phiphi and,
+   * by its root, C_phiT / C_phiE (camb/cmbmain.f90:122, :2254-2259); ALens_Fiducial > 0 replaces the lensing potential
+   * by the scaled template (camb/lensing.f90:52, :252-257).  ALens = 0 in a zero-filled struct is read as 1. */
+  double ALens, ALens_Fiducial;
 } galcamb_model;
 
 /* --- context --------------------------------------------------------------------------------------- */
@@ -149,6 +153,8 @@ int galcamb_lens_cls_(void);
  * ClTransferToCl (and lens_Cls if *do_lensing) for the batch.  No ODE, no line-of-sight work. */
 int galcamb_set_primordial_(const int* slot, const double* ScalarPowerAmp, const double* an, const double* n_run,
                             const double* n_runrun, const double* k_0_scalar);
+/* the lensing amplitudes of a resident slot (fast parameters like the primordial ones): next galcamb_transfers_to_powers_ */
+int galcamb_set_alens_(const int* slot, const double* ALens, const double* ALens_Fiducial);
 int galcamb_transfers_to_powers_(const int* do_lensing);
 int galcamb_get_lensed_cls_(const int* slot, int* lmax_lensed, double* Cl_lensed /* may be NULL */);
 
@@ -189,6 +195,7 @@ typedef struct galcamb_params {
   int WantTransfer, transfer_high_precision, transfer_k_per_logint, transfer_num_redshifts;
   double transfer_kmax;
   double transfer_redshifts[GALCAMB_MAX_TRANSFER_Z];
+  double ALens, ALens_Fiducial;                  /* camb/cmbmain.f90:122, camb/lensing.f90:52; defaults 1 and 0 */
 } galcamb_params;
 
 void galcamb_default_params_(galcamb_params* p);

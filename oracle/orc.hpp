@@ -185,6 +185,8 @@ struct Params {
   int transfer_k_per_logint = 0;
   int transfer_num_redshifts = 1;
   double transfer_redshifts[max_transfer_redshifts] = {0};
+  // lensing amplitudes (camb/cmbmain.f90:122, camb/lensing.f90:52; set by source/Calculator_CAMB.f90:130-131)
+  double ALens = 1, ALens_Fiducial = 0;
 };
 
 // ---------------------------------------------------------------- model state

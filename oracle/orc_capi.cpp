@@ -32,6 +32,7 @@ int orc_set(void* h, const char* name, double v) {
   I(Max_l) D(Max_eta_k) I(DoLensing) I(AccuratePolarization) I(AccurateReionization) I(MassiveNuMethod)
   I(DoLateRadTruncation) I(HighAccuracyDefault) D(AccuracyBoost) D(lSampleBoost) I(use_spline_template) I(nthreads)
   I(WantTransfer) I(transfer_high_precision) D(transfer_kmax) I(transfer_k_per_logint) I(transfer_num_redshifts)
+  D(ALens) D(ALens_Fiducial)
 #undef D
 #undef I
   if (n == "lAccuracyBoost") { P.lAccuracyBoost = (float)v; return 0; }

@@ -681,7 +681,7 @@ void CalcScalCls(Model& M) {
     ICL(j, 2) = ICL(j, 2) * dbletmp * ctnorm;
     ICL(j, 3) = ICL(j, 3) * dbletmp * std::sqrt(ctnorm);
     if (S > 2) {
-      const double ALens = 1.0;
+      const double ALens = M.P.ALens;  // camb/cmbmain.f90:122
       ICL(j, 4) = ALens * ICL(j, 4) * fourpi * (ell * ell * ell * ell);
       ICL(j, 5) = std::sqrt(ALens) * ICL(j, 5) * fourpi * (ell * ell * ell);
       ICL(j, 6) = std::sqrt(ALens) * ICL(j, 6) * fourpi * (ell * ell * ell) * std::sqrt(ctnorm);

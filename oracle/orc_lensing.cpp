@@ -83,6 +83,16 @@ int lens_Cls(Model& M) {
       CEE[l] = Tmpl(l, 1) * fac2 * sc;
       CTE[l] = Tmpl(l, 2) * fac2 * sc;
     }
+    if (Cphil3[Max_l + 1] > SP(1e-7)) {  // :243-249
+      GlobalError(M, "You need to normalize the high-L template so it is dimensionless", error_norm_lensing);
+      return M.error_flag;
+    }
+  }
+  if (M.P.ALens_Fiducial > 0) {  // :252-257
+    for (int l = 2; l <= lmax; l++) {
+      const double sc = (2 * l + 1) / (4 * pi) * 2 * pi / (l * (l + 1));
+      Cphil3[l] = sc * Tmpl(l, 3) * M.P.ALens_Fiducial;
+    }
   }
   std::vector<double> lens_contrib((size_t)4 * (lmax_lensed + 1), 0.0);  // [type 1..4][l]
   auto LC = [&](int t, int l) -> double& { return lens_contrib[(size_t)(t - 1) * (lmax_lensed + 1) + l]; };

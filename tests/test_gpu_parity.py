@@ -135,6 +135,21 @@ def test_three_source_variants_against_oracle(gpu, kw, lmax):
     _, cl2 = gpu.Cls(0)
     assert np.max(np.abs(cl2[:2] / o.Cl()[:2] - 1)) < TOL_CL
     check_lensed(gpu.Cl_lensed(0), o.Cl_lensed(), TOL_CL)
+    # the lensing amplitudes CosmoMC sets before every call (source/Calculator_CAMB.f90:130-131): ALens scales C_phiphi and,
+    # by its root, the phi-T / phi-E spectra (camb/cmbmain.f90:2254-2259); ALens_Fiducial puts the scaled template potential
+    # in place of the computed one (camb/lensing.f90:252-257)
+    for al, alf in ((1.3, 0.0), (1.0, 1.1)):
+        o.set(ALens=al, ALens_Fiducial=alf)
+        o.stage("cls", "lensing")
+        gpu.set_alens(0, al, alf)
+        gpu.TransfersToPowers(do_lensing=True)
+        _, cl3 = gpu.Cls(0)
+        assert np.max(np.abs(cl3[3] / o.Cl()[3] - 1)) < TOL_CL
+        assert np.max(np.abs(cl3[3] / cl2[3] / al - 1)) < 1e-12 and relmax(cl3[4], np.sqrt(al) * cl2[4]) < 1e-12
+        check_lensed(gpu.Cl_lensed(0), o.Cl_lensed(), TOL_CL)
+    assert gpu.evolve_stats()["rhs_executed"] == n_before
+    o.set(ALens=1.0, ALens_Fiducial=0.0)
+    gpu.set_alens(0, 1.0, 0.0)
 
 
 def test_config3_lensed_accuracyboost2_lmax5000(gpu):
