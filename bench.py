@@ -419,10 +419,10 @@ def main():
         g.L.galcamb_fp64_peak_(ctypes.c_void_p(pk.ctypes.data))  # FP64 FMA micro-benchmark on this GPU, now
         fp64_peak = float(pk[0]) if pk[0] > 0 else 37.2
         t_los = ev["los"] / args.steps * 1e-3
-        traffic, traffic_src = None, "no ncu capture of this build on file"
+        traffic, traffic_src = None, "no ncu capture on file"
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r2_k1_traffic.json")))
-            traffic = tr["dram_bytes_per_spectrum"] * B
+            traffic = tr["dram_bytes_per_spectrum"] * B  # measured at batch tr["batch"]; scaled to this batch per spectrum
             traffic_src = tr["source"]
         except Exception:
             pass
@@ -463,6 +463,20 @@ def main():
             pts, _ = oracle_valid_points(max(8, 2 * cores) + 2, SEED)
             cpu_reference_rate(pts[:2])  # warm-up + layout choice
             r, ccores, lanes, tpm, dtc, nd = cpu_reference_rate(pts[2:])
+            if "latency" in line:
+                # the same chain-step call on the host: one model, OpenMP over k like the reference (cmbmain.f90:201-206,
+                # :263-267, lensing.f90:288), all cores; parameters -> lensed C_l, Bessel tables cached as in the reference
+                Oracle = _oracle_class()
+                oc = Oracle(nthreads=cores, DoLensing=1, DoLateRadTruncation=0, lmax=2650, Num_Nu_massive=3, Num_Nu_massless=0.046,
+                            **meta["params"])
+                tc = []
+                for _ in range(4):
+                    t7 = time.perf_counter()
+                    oc.run(reuse_bessels=True)
+                    oc.stage("lensing")
+                    tc.append(1e3 * (time.perf_counter() - t7))
+                line["latency"]["cpu_ms_per_call"] = float(np.median(tc[1:]))
+                line["latency"]["cpu_threads"] = cores
             line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": ccores, "kind": "port",
                                     "sample": "%.1f s of oracle runs (%d distinct points, parameters -> C_l), %d models side by side x %d "
                                               "OpenMP threads, oracle built %s" % (dtc, nd, lanes, tpm, "-O3 -march=native" if _cpu.get("native") else "-O3 (portable)")}
