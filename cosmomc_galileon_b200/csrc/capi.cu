@@ -21,7 +21,10 @@
 
 #include "../../include/galcamb.h"
 #include "model.h"
+#include "pack.h"
 
+// packed tables of a model view handed out by the pre-stage (csrc/prestage.cu), or nullptr
+extern "C" const double* gc_prestage_prepacked(const galcamb_model* m, size_t* n, gcpack::Info* info);
 extern "C" void gc_upload_constants();
 extern "C" cudaError_t gc_launch_evolve(const DevModel*, const int2*, int, int, int, unsigned*, int*, unsigned long long*, cudaStream_t);
 extern "C" int gc_evolve_warps_per_cta(int);
@@ -78,6 +81,7 @@ struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[10]{};
+  cudaEvent_t ev_block = nullptr;  // blocking-sync event: the host thread sleeps through the long K1 launch instead of spinning
   // Bessel tables
   int nl = 0, nx = 0, kmaxfile = 0;
   double bess_boost = 0;
@@ -168,34 +172,6 @@ int fail(int code, const char* msg) {
   return code;
 }
 
-// natural cubic spline, c[i] = y''(x_i)/2 (the representation gsl_interp_cspline keeps)
-void natural_spline_c(const std::vector<double>& xa, const std::vector<double>& ya, std::vector<double>& c) {
-  const int n = (int)xa.size();
-  const int sys = n - 2;
-  c.assign(n, 0.0);
-  std::vector<double> g_(sys), diag(sys), off(sys), al(sys), ga(sys), z(sys);
-  for (int i = 0; i < sys; i++) {
-    const double h_i = xa[i + 1] - xa[i], h_ip1 = xa[i + 2] - xa[i + 1];
-    const double yd_i = ya[i + 1] - ya[i], yd_ip1 = ya[i + 2] - ya[i + 1];
-    const double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0, g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
-    off[i] = h_ip1;
-    diag[i] = 2.0 * (h_ip1 + h_i);
-    g_[i] = 3.0 * (yd_ip1 * g_ip1 - yd_i * g_i);
-  }
-  al[0] = diag[0];
-  ga[0] = off[0] / al[0];
-  for (int i = 1; i < sys - 1; i++) {
-    al[i] = diag[i] - off[i - 1] * ga[i - 1];
-    ga[i] = off[i] / al[i];
-  }
-  if (sys > 1) al[sys - 1] = diag[sys - 1] - off[sys - 2] * ga[sys - 2];
-  z[0] = g_[0];
-  for (int i = 1; i < sys; i++) z[i] = g_[i] - ga[i - 1] * z[i - 1];
-  for (int i = 0; i < sys; i++) z[i] = z[i] / al[i];
-  c[sys] = z[sys - 1];
-  for (int i = sys - 2; i >= 0; i--) c[i + 1] = z[i] - ga[i] * c[i + 2];
-}
-
 // BessRanges of camb/bessels.f90:68-76: five adjacent, non-overlapping regions, so the general merge rules of
 // Ranges_Add (camb/utils.F90:206-466) reduce to "n = max(1,int(span/delta + 1 - 0.1)), step = span/n" per region.
 void build_bess_ranges(int kmaxfile, double boost, GcRegions& R, std::vector<double>& xs) {
@@ -264,6 +240,7 @@ int galcamb_init_(const int* device) {
   CK(cudaSetDevice(g.device));
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   for (auto& e : g.ev) CK(cudaEventCreate(&e));
+  CK(cudaEventCreateWithFlags(&g.ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
   gc_upload_constants();
   gc_upload_constants_batch();
   gc_upload_constants_tr();
@@ -308,6 +285,8 @@ void galcamb_free_(void) {
                   (void*)g.d_lens_status})
     if (p) cudaFree(p);
   for (auto& e : g.ev) cudaEventDestroy(e);
+  if (g.ev_block) cudaEventDestroy(g.ev_block);
+  g.ev_block = nullptr;
   cudaStreamDestroy(g.stream);
   g = Ctx();  // the context object stays registered for its device; a later galcamb_init_ sets it up again
 }
@@ -515,49 +494,23 @@ static int pack_model(int islot, const galcamb_model* m) {
   }
   s.lmax = m->lmax;
   s.ntype = D.SourceNum > 2 ? 6 : 3;
-  // ---- pack the tables
-  const int ngal = m->use_galileon ? m->ngal + 1 : 0;  // + the linearly extrapolated node of galileon.cc:677-679
-  D.ngal = ngal;
-  const size_t n_th = (size_t)m->nthermo * 5, n_pm = m->nthermo, n_ts = (size_t)m->nt * 8, n_gal = (size_t)ngal * 5;
-  const size_t total = n_th + n_pm + n_ts + n_gal + m->nk + 2 * (size_t)m->nq + (size_t)D.nk_tr;
+  // ---- pack the tables (csrc/pack.h); a model that comes out of the library's own pre-stage was packed there already, on
+  // the pre-stage threads and -- in the pipelined form -- behind the device work of the previous batch
+  gcpack::Info I;
+  gcpack::sizes(m, D.nk_tr, I);
+  D.ngal = I.ngal;
+  const size_t n_th = I.n_th, n_pm = I.n_pm, n_ts = I.n_ts, n_gal = I.n_gal, total = I.total;
   if (s.ensure_staging(total)) return fail(100, "cudaMallocHost staging");
-  double* p = s.staging;
-  for (int i = 0; i < m->nthermo; i++) {
-    p[i * 5 + 0] = m->cs2[i]; p[i * 5 + 1] = m->dcs2[i]; p[i * 5 + 2] = m->dotmu[i];
-    p[i * 5 + 3] = m->ddotmu[i]; p[i * 5 + 4] = m->dddotmu[i];
+  size_t pre_n = 0;
+  gcpack::Info preI;
+  if (const double* pre = gc_prestage_prepacked(m, &pre_n, &preI); pre && pre_n == total) {
+    std::memcpy(s.staging, pre, total * sizeof(double));
+    I = preI;
+  } else {
+    gcpack::tables(m, D.nk_tr, s.staging, I);
   }
-  p += n_th;
-  {
-    double mn = m->dotmu[0];
-    for (int i = 0; i < m->nthermo; i++) { mn = std::min(mn, m->dotmu[i]); p[i] = mn; }
-  }
-  p += n_pm;
-  for (int i = 0; i < m->nt; i++) {
-    p[i * 8 + 0] = m->tau[i]; p[i * 8 + 1] = m->dtau[i]; p[i * 8 + 2] = m->vis[i]; p[i * 8 + 3] = m->dvis[i];
-    p[i * 8 + 4] = m->ddvis[i]; p[i * 8 + 5] = m->expmmu[i]; p[i * 8 + 6] = m->opac[i]; p[i * 8 + 7] = m->dopac[i];
-  }
-  p += n_ts;
-  if (ngal) {
-    const int nb1 = m->ngal;  // nb+1 tabulated points, ascending a
-    std::vector<double> a(ngal), hh(ngal), xx(ngal), ch, cx;
-    for (int i = 0; i < nb1; i++) { a[i] = m->gal_a[i]; hh[i] = m->gal_h[i]; xx[i] = m->gal_x[i]; }
-    // galileon.cc:677: intvar_interp[nb+1] = 1./q with q the geometric ratio; a[nb] = 1 so q = a[nb-1] exactly
-    a[nb1] = 1. / (a[nb1 - 2] / a[nb1 - 1]);
-    hh[nb1] = (hh[nb1 - 1] - hh[nb1 - 2]) / (a[nb1 - 1] - a[nb1 - 2]) * (a[nb1] - a[nb1 - 2]) + hh[nb1 - 2];
-    xx[nb1] = (xx[nb1 - 1] - xx[nb1 - 2]) / (a[nb1 - 1] - a[nb1 - 2]) * (a[nb1] - a[nb1 - 2]) + xx[nb1 - 2];
-    natural_spline_c(a, hh, ch);
-    natural_spline_c(a, xx, cx);
-    for (int i = 0; i < ngal; i++) {
-      p[i * 5 + 0] = a[i]; p[i * 5 + 1] = hh[i]; p[i * 5 + 2] = ch[i]; p[i * 5 + 3] = xx[i]; p[i * 5 + 4] = cx[i];
-    }
-    D.gal_a0 = a[0];
-    D.gal_lnq_inv = (nb1 - 1) / std::log(a[nb1 - 1] / a[0]);
-  }
-  p += n_gal;
-  std::copy(m->k, m->k + m->nk, p); p += m->nk;
-  std::copy(m->q, m->q + m->nq, p); p += m->nq;
-  std::copy(m->dq, m->dq + m->nq, p); p += m->nq;
-  if (D.nk_tr) { std::copy(m->k_transfer, m->k_transfer + D.nk_tr, p); p += D.nk_tr; }
+  D.gal_a0 = I.gal_a0;
+  D.gal_lnq_inv = I.gal_lnq_inv;
   s.m_nk_tr = D.nk_tr;
   s.total = total; s.n_th = n_th; s.n_pm = n_pm; s.n_ts = n_ts; s.n_gal = n_gal; s.m_nk = m->nk; s.m_nq = m->nq; s.m_lmax = m->lmax;
   return 0;
@@ -793,7 +746,10 @@ int galcamb_evolve_sources_(void) {
   CK(cudaMemcpyAsync(st.data(), g.d_status, nitems * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
   unsigned long long c[24];
   CK(cudaMemcpyAsync(c, g.d_counters, 24 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaStreamSynchronize(g.stream));
+  // K1 runs for seconds on a large batch: wait on a blocking-sync event so that this thread's core stays free for the
+  // host pre-stage of the next batch (one process per GPU: N spinning threads are N cores less for it)
+  CK(cudaEventRecord(g.ev_block, g.stream));
+  CK(cudaEventSynchronize(g.ev_block));
   float ms = 0;
   cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]);
   g.ms[0] = ms;

@@ -118,10 +118,12 @@ int Background::stability(double a, const double y[3]) {
   return 0;
 }
 
-// Fehlberg 4(5) embedded pair (published tableau), first-same-as-last derivative handed in and out like GSL's rkf45
+// Fehlberg 4(5) embedded pair (published tableau); the derivative at the start of the step is handed in.  (GSL's rkf45 also
+// evaluates the derivative at the end of every trial step for its caller; the y-error controller used here never reads
+// it, so it is not computed: one right-hand side in seven less, bit-identical results.)
 struct Rkf45 {
   const Background& B;
-  void step(double t, double h, double y[3], double yerr[3], const double k1[3], double dydt_out[3]) const {
+  void step(double t, double h, double y[3], double yerr[3], const double k1[3]) const {
     static const double c[] = {1.0 / 4.0, 3.0 / 8.0, 12.0 / 13.0, 1.0, 1.0 / 2.0};
     static const double a2[] = {1.0 / 4.0};
     static const double a3[] = {3.0 / 32.0, 9.0 / 32.0};
@@ -146,7 +148,6 @@ struct Rkf45 {
       const double d = b[0] * k[0][i] + b[2] * k[2][i] + b[3] * k[3][i] + b[4] * k[4][i] + b[5] * k[5][i];
       y[i] += h * d;
     }
-    B.rhs(t + h, y, dydt_out);
     for (int i = 0; i < 3; i++)
       yerr[i] = h * (e[0] * k[0][i] + e[2] * k[2][i] + e[3] * k[3][i] + e[4] * k[4][i] + e[5] * k[5][i]);
   }
@@ -159,12 +160,12 @@ void Background::evolve_apply(double& t, double t1, double& h, double y[3]) cons
   const double t0 = t, dt = t1 - t0;
   double h0 = h;
   const double y0[3] = {y[0], y[1], y[2]};
-  double yerr[3], dydt_in[3], dydt_out[3];
+  double yerr[3], dydt_in[3];
   rhs(t0, y, dydt_in);
   for (;;) {
     const bool final_step = (dt >= 0.0 && h0 > dt) || (dt < 0.0 && h0 < dt);
     if (final_step) h0 = dt;
-    stepper.step(t0, h0, y, yerr, dydt_in, dydt_out);
+    stepper.step(t0, h0, y, yerr, dydt_in);
     t = final_step ? t1 : t0 + h0;
     const double h_old = h0;
     double rmax = 2.2250738585072014e-308;

@@ -15,15 +15,18 @@
 // galcamb_batch_cls_ take.  Plain C++ (no device code); arrays are 1-based like the reference.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/galcamb.h"
+#include "pack.h"
 
 int gc_galileon_background(double omegar, double omegam, double h0, double c2, double c3in, double c4in, double cG, int neig,
                            const double* grhormass, const double* nu_masses, const double* nu_tab, double dlnam, double* coef,
@@ -518,6 +521,10 @@ struct Model {
   int kmaxfile = 0;
   // matter transfer functions: output times (ascending) and the wavenumbers beyond the source grid
   std::vector<double> tautf, k_transfer;
+  double prof_bg_ms = 0, prof_rec_ms = 0;  // GALCAMB_PRESTAGE_PROFILE
+  // the tables in the device layout (csrc/pack.h), packed by the pre-stage thread that built the point
+  std::vector<double> packed;
+  gcpack::Info pinfo;
 
   int fail(int id, const char* msg) {
     status = id;
@@ -660,9 +667,11 @@ int Model::params_set() {
     const double omegar = (grhog + grhornomass) / grhom, omegam = P.omegab + P.omegac, hub = P.H0 / c * 1000;
     gal_h0 = hub;
     gal_orad = omegar;
+    const auto tb0 = std::chrono::steady_clock::now();
     const int st = gc_galileon_background(omegar, omegam, hub, P.c2, P.c3, P.c4, P.cG, Nu_mass_eigenstates, grhormass + 1,
                                           nu_masses + 1, g_nu.rows.empty() ? nullptr : g_nu.rows.data(), g_nu.dlnam, gal_coef, gal_a,
                                           gal_h, gal_x);
+    prof_bg_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count();
     if (st != 0) return fail(6, "Didn't compute background successfully");
     // natural-spline coefficients of hbar (c = y''/2, gsl_interp_cspline): spline_natural gives y''
     const int n = (int)gal_a.size();
@@ -972,7 +981,9 @@ int Model::init_vars() {
     taumin = std::fmin(taumin, 1.e-3 / mx / adotrad);
   }
   // inithermo(taumin, tau0), camb/modules.f90:2787-3103
+  const auto tr0 = std::chrono::steady_clock::now();
   if (int rc = recombination()) return rc;
+  prof_rec_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count();
   const int nt = NTHERMO;
   std::vector<double> tb(nt + 1), c2(nt + 1), xe(nt + 1), dc2(nt + 1), dm(nt + 1), ddm(nt + 1), sdm(nt + 1), emmu(nt + 1), demmu(nt + 1),
       dddm(nt + 1), ddddm(nt + 1);
@@ -1287,11 +1298,21 @@ void Model::l_samples() {
 int Model::run() {
   status = 0;
   err.clear();
+  static const bool prof = getenv("GALCAMB_PRESTAGE_PROFILE") != nullptr;  // per-phase wall clock of every point to stderr
+  const auto t0 = std::chrono::steady_clock::now();
   if (int rc = params_set()) return rc;
+  const auto t1 = std::chrono::steady_clock::now();
   l_samples();
   if (int rc = init_vars()) return rc;
+  const auto t2 = std::chrono::steady_clock::now();
   k_grids();
   transfer_grid();
+  if (prof) {
+    const auto t3 = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "[prestage] params_set %.2f ms (background %.2f) init_vars %.2f ms (recfast %.2f) grids %.2f ms\n", ms(t0, t1), prof_bg_ms,
+            ms(t1, t2), prof_rec_ms, ms(t2, t3));
+  }
   return 0;
 }
 
@@ -1305,6 +1326,13 @@ static std::vector<galcamb_params> g_async_params;
 static std::thread g_async;
 static int g_async_rc = 0;
 static int g_host_threads = 0;
+// cs2 table address of every point of the current batch -> its index (galcamb_model views carry no back pointer)
+static std::unordered_map<const double*, int> g_by_table;
+static void index_current_batch() {
+  g_by_table.clear();
+  for (size_t i = 0; i < g_batch.size(); i++)
+    if (g_batch[i].status == 0 && !g_batch[i].packed.empty()) g_by_table[g_batch[i].cs2.data()] = (int)i;
+}
 
 static void fill_view(const Model& M, galcamb_model* m) {
   std::memset(m, 0, sizeof(*m));
@@ -1401,6 +1429,14 @@ static int prestage_into(std::vector<pre::Model>& batch, std::string& err, const
       const int i = next.fetch_add(1);
       if (i >= n) break;
       batch[i].run();
+      if (batch[i].status == 0) {  // device layout of the tables, ready for galcamb_set_model_ / galcamb_batch_upload_
+        galcamb_model v;
+        fill_view(batch[i], &v);
+        const int nk_tr = v.WantTransfer ? v.nk_transfer : 0;
+        gcpack::sizes(&v, nk_tr, batch[i].pinfo);
+        batch[i].packed.resize(batch[i].pinfo.total);
+        gcpack::tables(&v, nk_tr, batch[i].packed.data(), batch[i].pinfo);
+      }
       batch[i].zrec = std::vector<double>();  // the recombination history is only needed up to inithermo
       batch[i].xrec = std::vector<double>();
       batch[i].dxrec = std::vector<double>();
@@ -1425,7 +1461,9 @@ int galcamb_prestage_(const galcamb_params* params, const int* n, const int* nth
     pre::g_err = "n < 1";
     return 5;
   }
-  return prestage_into(pre::g_batch, pre::g_err, params, *n, *nthreads);
+  const int rc = prestage_into(pre::g_batch, pre::g_err, params, *n, *nthreads);
+  pre::index_current_batch();
+  return rc;
 }
 
 // Pipelined form: galcamb_prestage_async_ starts the same work on a second buffer and returns at once -- the device
@@ -1449,8 +1487,19 @@ int galcamb_prestage_wait_(void) {
   g_async.join();
   g_batch.swap(g_next);
   g_next.clear();
+  index_current_batch();
   g_err = g_next_err;
   return g_async_rc;
+}
+
+// the packed tables of a model view handed out by galcamb_prestage_model_ (csrc/capi.cu pack_model), or nullptr
+const double* gc_prestage_prepacked(const galcamb_model* m, size_t* n, gcpack::Info* info) {
+  const auto it = pre::g_by_table.find(m->cs2);
+  if (it == pre::g_by_table.end()) return nullptr;
+  const pre::Model& M = pre::g_batch[it->second];
+  *n = M.packed.size();
+  *info = M.pinfo;
+  return M.packed.data();
 }
 
 int galcamb_prestage_count_(void) { return (int)pre::g_batch.size(); }
@@ -1486,6 +1535,7 @@ int galcamb_prestage_lsamples_(const int* i, int* nl, int* ls, int* kmaxfile) {
 }
 
 void galcamb_prestage_free_(void) {
+  pre::g_by_table.clear();
   pre::g_batch.clear();
   pre::g_batch.shrink_to_fit();
 }

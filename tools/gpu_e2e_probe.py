@@ -1,5 +1,5 @@
 """Where the time of one end-to-end step (parameters -> C_l through galcamb_prestaged_to_cls_) goes: the bench's e2e
-loop with the library's host-phase timers.  usage: python tools/gpu_e2e_probe.py [batch] [steps]"""
+loop with the library's host-phase timers.  usage: python tools/gpu_e2e_probe.py [batch] [steps] [host threads]"""
 import os
 import sys
 import time
@@ -15,7 +15,7 @@ from cosmomc_galileon_b200.proposal import valid_points  # noqa: E402
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-    threads = os.cpu_count() or 8
+    threads = int(sys.argv[3]) if len(sys.argv) > 3 else (os.cpu_count() or 8)
     g = GalCamb(0)
     g.set_host_threads(threads)
     g.set_template(np.fromfile(os.path.join(ROOT, "tests", "golden", "highL_template.f64")).reshape(7999, 4).T.copy())
