@@ -42,6 +42,9 @@
 #define GC_HIER_UNROLL 4
 #endif
 constexpr int kHierUnroll = GC_HIER_UNROLL;
+#ifndef GC_EARLY_FIELD_EQ
+#define GC_EARLY_FIELD_EQ 1
+#endif
 
 namespace gc {
 
@@ -87,15 +90,25 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
   // massive-neutrino background at this a (shared by MassiveNuVars, GetdHdX and dtauda)
   double rhonu[GC_EV_NU], pnu[GC_EV_NU];
   for (int i = 0; i < M.n_eig; i++) Nu_background(M, a * M.nu_masses[i], rhonu[i], pnu[i]);
-  double grhov_t = 0, xgal = 0, grhogal_t = 0, hbar = 0;
-  GalFast F;
-  const GalConst GC{M.c2, M.c3, M.c4, M.c5, M.cG, M.h0, M.orad};
+  double grhov_t = 0, xgal = 0, hbar = 0;
+  // Galileon terms as linear forms in the perturbations (galileon_fast.cuh).  All of their coefficients are formed HERE,
+  // from the background record F of this (a, hbar, x): F itself (45 doubles) is then dead, and only the 7 + 6 (+ 5 in
+  // tight coupling) coefficients stay live through the hierarchy loops below instead of being spilled to local memory.
+  double chi_p = 0, chi_d = 0, chi_g = 0, chi_e = 0, q_d = 0, q_p = 0, q_g = 0, gpresgal_t = 0;
+  GalPhi2Lin D2{0, 0, 0, 0, 0, 0};
+  GalPiLin P2{0, 0, 0, 0, 0};
   if (gal) {
     gal_HX(M, a, hbar, xgal);
     double lam_nu = 0;
     for (int i = 0; i < M.n_eig; i++) lam_nu += M.grhormass[i] * pnu[i];
+    const GalConst GC{M.c2, M.c3, M.c4, M.c5, M.cG, M.h0, M.orad};
+    GalFast F;
     gal_fast_background(GC, a, hbar, xgal, lam_nu, k, F);
-    grhogal_t = F.grhogal;
+    gpresgal_t = F.gpresgal;
+    chi_p = F.chi_p; chi_d = F.chi_d; chi_g = F.chi_g; chi_e = F.chi_e;
+    q_d = F.q_d; q_p = F.q_p; q_g = F.q_g;
+    gal_fast_dphisecond_lin(GC, F, D2);
+    if (e.TightCoupling) gal_fast_Pigal_lin(GC, F, P2);
   } else {
     grhov_t = M.grhov * a2;
   }
@@ -104,7 +117,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
   double gpres = 0;
   gpres = gpres + (grhog_t + grhor_t) / 3;
   if (gal)
-    gpres = gpres + F.gpresgal;
+    gpres = gpres + gpresgal_t;
   else
     gpres = gpres + grhov_t * (-1.0);
   double grho_matter = grhob_t + grhoc_t;
@@ -151,7 +164,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
   double z = 0, dz, clxr, qr, pir, clxg, qg, pig = 0, dgrhogal_t;
   if (e.no_nu) {
     if (gal) {
-      dgrhogal_t = gal_fast_Chigal(F, dgrho, etak, dphi, dphiprime);
+      dgrhogal_t = (chi_p * dphiprime + chi_d * dphi + chi_g * dgrho + chi_e * etak);
       z = (0.5 * (dgrho + dgrhogal_t) * ik + etak) * iadotoa;
       dz = -adotoa * z - 0.5 * (dgrho + dgrhogal_t) * ik;
     } else {
@@ -169,7 +182,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
   if (e.no_phot) {
     if (!e.no_nu) {
       if (gal) {
-        dgrhogal_t = gal_fast_Chigal(F, dgrho, etak, dphi, dphiprime);
+        dgrhogal_t = (chi_p * dphiprime + chi_d * dphi + chi_g * dgrho + chi_e * etak);
         z = (0.5 * (dgrho + dgrhogal_t) * ik + etak) * iadotoa;
         dz = -adotoa * z - 0.5 * (dgrho + dgrhogal_t) * ik;
       } else {
@@ -194,9 +207,9 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
   const double pb43 = 4.0 / 3 * photbar;
   AT(ayp, 1) = adotoa * a;
   if (gal) {
-    dgrhogal_t = gal_fast_Chigal(F, dgrho, etak, dphi, dphiprime);
+    dgrhogal_t = (chi_p * dphiprime + chi_d * dphi + chi_g * dgrho + chi_e * etak);
     dgrho = dgrho + dgrhogal_t;
-    dgq = dgq + gal_fast_qgal(F, dgq, dphi, dphiprime);
+    dgq = dgq + (q_d * dphi + q_p * dphiprime + q_g * dgq);
   }
   z = (0.5 * dgrho * ik + etak) * iadotoa;
   const double sigma = (z + 1.5 * dgq * ik2);
@@ -215,7 +228,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
     const double slip = -(2 * adotoa * ipb + dopacity * iop) * (vb - 3.0 / 4 * qg) +
                         (-adotdota * vb - k / 2 * adotoa * clxg + k * (cs2 * clxbdot - clxgdot / 4)) * (iop * ipb);
     double dgs = grhog_t * pig + grhor_t * pir;
-    if (gal) dgs = dgs + gal_fast_Pigal(GC, F, dgrho, dgq, dgs, etak, dphi);
+    if (gal) dgs = dgs + (P2.d * dphi + P2.pi * dgs + P2.g * dgrho + P2.q * dgq + P2.e * etak);
     const double sigmadot = -2 * adotoa * sigma - dgs * ik + etak;
     qgdot = k * (clxg / 4.0 - pig / 2.0) + opacity * slip;
     const double dop = dopacity * iop2;
@@ -231,6 +244,18 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
     vbdot = -adotoa * vb + cs2 * k * clxb - photbar * opacity * (4.0 / 3 * vb - qg);
   }
   AT(ayp, 5) = vbdot;
+#if GC_EARLY_FIELD_EQ
+  // The Galileon field equation (camb/equations_galileon.f90:2516-2521) here, ahead of the multipole hierarchies: all of
+  // its inputs are known, and its 6 + 12 operands need not stay live through the loops below (the stores are to distinct
+  // elements of y', so their order is free).
+  const double clxrdot = e.no_nu ? 0.0 : -k * (4.0 / 3.0 * z + qr);
+  if (gal) {
+    const double dotdeltaf = grhob_t * (clxbdot - 3 * adotoa * clxb) + grhoc_t * (clxcdot - 3 * adotoa * clxc) +
+                             grhor_t * (clxrdot - 4 * adotoa * clxr) + grhog_t * (clxgdot - 4 * adotoa * clxg);
+    AT(ayp, e.w_ix) = dphiprime;
+    AT(ayp, e.w_ix + 1) = D2.p * dphiprime + D2.d * dphi + D2.g * dgrho + D2.q * dgq + D2.f * dotdeltaf + D2.e * etak;
+  }
+#endif
   if (!e.no_phot) {
     AT(ayp, e.g_ix) = clxgdot;
     qgdot = 4.0 / 3 * (-vbdot - adotoa * vb + cs2 * k * clxb) / pb43 + denlk(e, 1) * clxg - denlk2(e, 1) * pig;
@@ -270,9 +295,13 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
   }
   // clxrdot is read uninitialised by the reference when no_nu_multpoles (:2517 vs :2482); pinned to 0 like
   // the oracle (the value of its defining expression under qr = -4z/3).
+#if !GC_EARLY_FIELD_EQ
   double clxrdot = 0;
+#endif
   if (!e.no_nu) {
+#if !GC_EARLY_FIELD_EQ
     clxrdot = -k * (4.0 / 3.0 * z + qr);
+#endif
     AT(ayp, e.r_ix) = clxrdot;
     AT(ayp, e.r_ix + 1) = denlk(e, 1) * clxr - denlk2(e, 1) * pir;
     if (e.high_ktau) {
@@ -293,12 +322,14 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
       }
     }
   }
+#if !GC_EARLY_FIELD_EQ
   if (gal) {
     const double dotdeltaf = grhob_t * (clxbdot - 3 * adotoa * clxb) + grhoc_t * (clxcdot - 3 * adotoa * clxc) +
                              grhor_t * (clxrdot - 4 * adotoa * clxr) + grhog_t * (clxgdot - 4 * adotoa * clxg);
     AT(ayp, e.w_ix) = dphiprime;
-    AT(ayp, e.w_ix + 1) = gal_fast_dphisecond(GC, F, dgrho, dgq, etak, dphi, dphiprime, dotdeltaf);
+    AT(ayp, e.w_ix + 1) = D2.p * dphiprime + D2.d * dphi + D2.g * dgrho + D2.q * dgq + D2.f * dotdeltaf + D2.e * etak;
   }
+#endif
   if (M.Num_Nu_massive == 0) return;
   for (int nu_i = 0; nu_i < M.n_eig; nu_i++) {
     if (e.MassiveNuApprox[nu_i]) {
@@ -532,6 +563,27 @@ __device__ __forceinline__ int combine_uniform(int i, int nend, const double* __
   return i;
 }
 
+// Row R of the tableau through combine_uniform: the compact column list of the row (ascending j, as the sums run) and its
+// coefficients are compile-time selections -- registers and constant-bank operands, no run-time-indexed local arrays.
+// Columns: rows 0..5 read k1..k(R+1) (row 5: k1..k5), row 6 skips k6, row 7 (trial solution + error) skips k2.
+template <int R>
+__device__ __forceinline__ int combine_uniform_row(int i, int nend, const double* __restrict__ y, double* __restrict__ w9,
+                                                   const double* const* kc, double temp, bool stash, bool stash_k1,
+                                                   double* __restrict__ ys, double* __restrict__ ks, double& errn, double& ynew) {
+  constexpr int NC = R == 0 ? 1 : R == 1 ? 2 : R == 2 ? 3 : R == 3 ? 4 : R <= 5 ? 5 : R == 6 ? 6 : 7;
+  constexpr int U = NC >= 6 ? 4 : 8;
+  const double* kk[NC];
+  double cfk[NC], cek[NC];
+#pragma unroll
+  for (int j = 0; j < NC; j++) {
+    const int c = R == 6 ? (j < 5 ? j : 6) : R == 7 ? (j == 0 ? 0 : j + 1) : j;
+    kk[j] = kc[c];
+    cfk[j] = c_row[R][c];
+    cek[j] = R == 7 ? c_err[c] : 0.0;
+  }
+  return combine_uniform<NC, U, R == 0, R == 7>(i, nend, y, w9, kk, cfk, cek, temp, stash, stash_k1, ys, ks, errn, ynew);
+}
+
 // ONE stage-combination routine for every row of the tableau, executed by the whole warp together: each lane brings
 // its own row (L.crow), length and scale, so lanes that sit in different Runge-Kutta stages -- the normal state of
 // a warp whose 32 lanes integrate 32 different cosmologies -- share one pass over the columns instead of running
@@ -570,29 +622,17 @@ __device__ __forceinline__ void combine(Lane& L) {
   const int nmin = __reduce_min_sync(0xffffffffu, on ? n : 0x7fffffff);
   int i = 1;
   if (same_row && nmin >= 4 && nmin != 0x7fffffff) {
-    // compact column list of the row (ascending j, as the sums run)
-    const double* kk[7];
-    double cfk[7], cek[7];
-    int nc = 0;
-#pragma unroll
-    for (int c = 0; c < 8; c++)
-      if (umask & (1u << c)) {
-        if (nc < 7) {
-          kk[nc] = kc[c];
-          cfk[nc] = cf[c];
-          cek[nc] = ce[c];
-        }
-        nc++;
-      }
     if (on) {  // padding lanes of a short k group sit this out
-      const int r_u = r;
-      if (r_u == 0) i = combine_uniform<1, 8, true, false>(i, nmin, y, w9, kk, cfk, cek, temp, stash, stash_k1, ys, ks, errn, ynew);
-      else if (r_u == 7) i = combine_uniform<7, 4, false, true>(i, nmin, y, w9, kk, cfk, cek, temp, false, false, ys, ks, errn, ynew);
-      else if (nc == 2) i = combine_uniform<2, 8, false, false>(i, nmin, y, w9, kk, cfk, cek, temp, false, false, ys, ks, errn, ynew);
-      else if (nc == 3) i = combine_uniform<3, 8, false, false>(i, nmin, y, w9, kk, cfk, cek, temp, false, false, ys, ks, errn, ynew);
-      else if (nc == 4) i = combine_uniform<4, 8, false, false>(i, nmin, y, w9, kk, cfk, cek, temp, false, false, ys, ks, errn, ynew);
-      else if (nc == 5) i = combine_uniform<5, 8, false, false>(i, nmin, y, w9, kk, cfk, cek, temp, false, false, ys, ks, errn, ynew);
-      else if (nc == 6) i = combine_uniform<6, 4, false, false>(i, nmin, y, w9, kk, cfk, cek, temp, false, false, ys, ks, errn, ynew);
+      switch (r) {  // warp-uniform here
+        case 0: i = combine_uniform_row<0>(i, nmin, y, w9, kc, temp, stash, stash_k1, ys, ks, errn, ynew); break;
+        case 1: i = combine_uniform_row<1>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew); break;
+        case 2: i = combine_uniform_row<2>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew); break;
+        case 3: i = combine_uniform_row<3>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew); break;
+        case 4: i = combine_uniform_row<4>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew); break;
+        case 5: i = combine_uniform_row<5>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew); break;
+        case 6: i = combine_uniform_row<6>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew); break;
+        default: i = combine_uniform_row<7>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew); break;
+      }
     }
     {  // first element the uniform loops did not cover (same for every lane)
       const int ub = (umask & 0xe0u) ? 4 : 8;
