@@ -26,7 +26,7 @@ TRANSFER_SOURCES = ["evolve.cu", "evolve_batch.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FMAD = os.environ.get("GALCAMB_FMAD", "true")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=" + FMAD, "-std=c++17", "-Xcompiler",
-         "-fPIC", "-ccbin", "/usr/bin/g++"] + os.environ.get("GALCAMB_NVCC_EXTRA", "").split()
+         "-fPIC,-fno-math-errno", "-ccbin", "/usr/bin/g++"] + os.environ.get("GALCAMB_NVCC_EXTRA", "").split()
 
 
 def _stale(out, deps):

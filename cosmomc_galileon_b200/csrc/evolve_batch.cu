@@ -46,13 +46,119 @@ constexpr int kHierUnroll = GC_HIER_UNROLL;
 #define GC_EARLY_FIELD_EQ 1
 #endif
 
+#ifndef GC_STATE_CG
+#define GC_STATE_CG 0
+#endif
+// the derivative of the last stage (k8) is stored in k2's column (dead after row 6 of the tableau): 9 live columns
+// per lane instead of 10 in the L2-resident workspace
+#ifndef GC_K8_IN_K2
+#define GC_K8_IN_K2 1
+#endif
+// high multipoles of every hierarchy evaluated ahead of the Einstein / Galileon part of derivs() (see there)
+#ifndef GC_EARLY_HIER
+#define GC_EARLY_HIER 1
+#endif
+// stage combinations with two batches of loads in flight (see combine_uniform)
+#ifndef GC_COMBINE_PIPE
+#define GC_COMBINE_PIPE 0
+#endif
+
 namespace gc {
+
+// Read-only view of a workspace column for derivs(): with GC_STATE_CG the element loads bypass L1 (ld.global.cg), which
+// then holds only table rows, per-model constants and spilled registers instead of the once-read state stream.
+struct InCol {
+  const double* __restrict__ p;
+  __device__ __forceinline__ double operator[](int i) const {
+#if GC_STATE_CG
+    return __ldcg(p + i);
+#else
+    return p[i];
+#endif
+  }
+  __device__ __forceinline__ operator const double*() const { return p; }
+};
+
+// One pass over a run of `cnt` consecutive multipoles of a hierarchy, first column index ix0, first multipole l0:
+// y'(ix) = f(l, y(ix-1), y(ix), y(ix+1)).  All loads of a batch of U equations are issued together (U + 2 independent
+// loads, one exposed memory latency) before any arithmetic; the expressions themselves are the caller's, unchanged.
+// The last equation of a run is the truncation formula, which does not read y(ix+1): that element is not loaded.
+// skip_l: a multipole whose equation the caller evaluates elsewhere (nothing is stored for it).
+#ifndef GC_HIER_BATCH
+#define GC_HIER_BATCH 8
+#endif
+template <class F>
+__device__ __forceinline__ void hier_run(const InCol ay, double* __restrict__ ayp, int ix0, int l0, int cnt, int skip_l, F f) {
+  constexpr int U = GC_HIER_BATCH;
+  for (int c = 0; c < cnt; c += U) {
+    double v[U + 2];
+#pragma unroll
+    for (int u = 0; u < U + 2; u++) v[u] = (c + u <= cnt) ? AT(ay, ix0 + c + u - 1) : 0.0;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int l = l0 + c + u;
+      if (c + u < cnt && l != skip_l) AT(ayp, ix0 + c + u) = f(l, v[u], v[u + 1], v[u + 2]);
+    }
+  }
+}
+
+// Nu_Integrate_L012 (camb/equations_galileon.f90:1058-1107; evolve_device.cuh) for derivs(): density and flux moments
+// only, the loads of all momentum bins issued before the sums (same terms, same order).
+__device__ __forceinline__ void nu_moments_01(const DevModel& M, const EV& e, const InCol y, double a, int nu_i, double& drhonu,
+                                              double& fnu) {
+  const double am = a * M.nu_masses[nu_i];
+  const int nq = e.nq[nu_i], nqmax = M.nqmax;
+  const int ind = e.nu_ix[nu_i], step = e.lmaxnu_tau[nu_i] + 1, indp = e.nu_pert_ix;
+  double y0[GC_MAX_NQ], y1[GC_MAX_NQ];
+#pragma unroll
+  for (int iq = 0; iq < GC_MAX_NQ; iq++) {
+    const bool own = iq < nq, pert = !own && iq < nqmax;
+    y0[iq] = own ? AT(y, ind + iq * step) : 0.0;
+    y1[iq] = own ? AT(y, ind + iq * step + 1) : 0.0;
+    (void)pert;
+  }
+  double r0 = 0, r1 = 0, p0 = 0, p1 = 0;
+  if (nq < nqmax) {
+    r0 = AT(y, e.r_ix);
+    r1 = AT(y, e.r_ix + 1);
+    p0 = AT(y, indp);
+    p1 = AT(y, indp + 1);
+  }
+  drhonu = 0;
+  fnu = 0;
+#pragma unroll
+  for (int iq = 0; iq < GC_MAX_NQ; iq++) {
+    if (iq < nq) {
+      const double aq = am * M.inv_nu_q[iq];
+      const double e2 = 1.0 + aq * aq;
+      const double v = rsqrt(e2), iv = e2 * v;
+      const double ker = M.nu_int_kernel[iq];
+      drhonu = drhonu + ker * y0[iq] * iv;
+      fnu = fnu + ker * y1[iq];
+    }
+  }
+#pragma unroll
+  for (int iq = 0; iq < GC_MAX_NQ; iq++) {
+    if (iq >= nq && iq < nqmax) {
+      const double aq = am * M.inv_nu_q[iq];
+      const double e2 = 1.0 + aq * aq;
+      const double v = rsqrt(e2), iv = e2 * v;
+      const double r = M.nu_masses[nu_i] * M.inv_nu_q[iq];
+      const double pert_scale = (r * r) / 2;
+      const double ker = M.nu_int_kernel[iq];
+      const double tmp = ker * (r0 + pert_scale * p0);
+      drhonu = drhonu + tmp * iv;
+      fnu = fnu + ker * (r1 + pert_scale * p1);
+    }
+  }
+}
 
 // ---------------------------------------------------------------- derivs
 // camb/equations_galileon.f90:2098-2589.  ay / ayp are workspace columns.  Writes e.pig / e.pigdot during
 // tight coupling exactly as the reference does (its value at a switch is the one left by the LAST call).
 __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restrict__ ep, double tau,
-                                    const double* __restrict__ ay, double* __restrict__ ayp) {
+                                    const double* __restrict__ ay_, double* __restrict__ ayp) {
+  const InCol ay{ay_};
   // __restrict__ on every pointer: the state-vector stores below must not force reloads of the model constants
   // (global) or of the lane's layout descriptor (local) after each store.
   const DevModel& M = *Mp;
@@ -86,6 +192,53 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
       if (e.lmaxgpol > 2) y_e3 = AT(ay, e.polind + 3);
     }
   }
+  double cs2, opacity, dopacity = 0;
+  thermo(M, tau, cs2, opacity, e.TightCoupling ? &dopacity : nullptr);
+  const double cothxor = 1.0 / tau;
+#if GC_EARLY_HIER
+  // The equations of the high multipoles (l >= 3 of photons, polarisation, massless neutrinos; l = 1 and l >= 3 of every
+  // momentum bin of the massive neutrinos; the perturbative massive-neutrino hierarchy) read nothing but y, k, the opacity
+  // and tau: they are evaluated HERE, before the Einstein / Galileon part, while few registers are live -- whole runs of
+  // multipoles per exposed memory latency instead of a latency per statement under the register pressure further down.
+  // Every expression is the one of camb/equations_galileon.f90:2437-2589; the stores go to distinct elements of y'.
+  if (!e.no_phot && !e.TightCoupling) {
+    if (e.lmaxg > 2) {
+      const int lm = e.lmaxg;
+      hier_run(ay, ayp, e.g_ix + 3, 3, lm - 2, -1, [&](int l, double ym, double y0, double yp) {
+        return l < lm ? (denlk(e, l) * ym - denlk2(e, l) * yp) - opacity * y0 : k * ym - (lm + 1) * cothxor * y0 - opacity * y0;
+      });
+    }
+    if (e.lmaxgpol > 2) {
+      const int lm = e.lmaxgpol;
+      hier_run(ay, ayp, e.polind + 3, 3, lm - 2, -1, [&](int l, double ym, double y0, double yp) {
+        return l < lm ? -opacity * y0 + (denlk(e, l) * ym - polfack(e, l) * yp)
+                      : -opacity * y0 + k * e.poltruncfac * ym - (lm + 3) * cothxor * y0;
+      });
+    }
+  }
+  if (!e.no_nu && !e.high_ktau && e.lmaxnr > 2) {
+    const int lm = e.lmaxnr;
+    hier_run(ay, ayp, e.r_ix + 3, 3, lm - 2, -1, [&](int l, double ym, double y0, double yp) {
+      return l < lm ? (denlk(e, l) * ym - denlk2(e, l) * yp) : k * ym - (lm + 1) * cothxor * y0;
+    });
+  }
+  if (M.Num_Nu_massive != 0) {
+    for (int nu_i = 0; nu_i < M.n_eig; nu_i++) {
+      if (e.MassiveNuApprox[nu_i]) continue;
+      const int lm = e.lmaxnu_tau[nu_i];
+      int ind = e.nu_ix[nu_i];
+      for (int i = 1; i <= e.nq[nu_i]; i++) {
+        const double aq = a * M.nu_masses[nu_i] * M.inv_nu_q[i - 1];
+        const double v = rsqrt(1.0 + aq * aq);
+        // l = 1 .. lm of this momentum bin; l = 0 and l = 2 need z and sigma and follow below.  With lm = 2 only l = 1.
+        hier_run(ay, ayp, ind + 1, 1, lm == 2 ? 1 : lm, 2, [&](int l, double ym, double y0, double yp) {
+          return (l < lm || lm == 2) ? v * (denlk(e, l) * ym - denlk2(e, l) * yp) : k * v * ym - (lm + 1) * cothxor * y0;
+        });
+        ind = ind + lm + 1;
+      }
+    }
+  }
+#endif
   const double grhob_t = M.grhob * ia, grhoc_t = M.grhoc * ia, grhor_t = M.grhornomass * ia2, grhog_t = M.grhog * ia2;
   // massive-neutrino background at this a (shared by MassiveNuVars, GetdHdX and dtauda)
   double rhonu[GC_EV_NU], pnu[GC_EV_NU];
@@ -112,8 +265,6 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
   } else {
     grhov_t = M.grhov * a2;
   }
-  double cs2, opacity, dopacity = 0;
-  thermo(M, tau, cs2, opacity, e.TightCoupling ? &dopacity : nullptr);
   double gpres = 0;
   gpres = gpres + (grhog_t + grhor_t) / 3;
   if (gal)
@@ -133,7 +284,11 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
         clxnu = AT(ay, e.nu_ix[nu_i]);
         qnu = AT(ay, e.nu_ix[nu_i] + 2);
       } else {
+#if GC_EARLY_HIER
+        nu_moments_01(M, e, ay, a, nu_i, clxnu, qnu);
+#else
         Nu_Integrate_L012(M, e, ay, a, nu_i, clxnu, qnu, nullptr, nullptr);
+#endif
         qnu = qnu * irho;
         clxnu = clxnu * irho;
       }
@@ -159,7 +314,6 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
   }
   const double adotoa = sqrt(grhoa2 * (1.0 / 3.0)) * ia;  // 1/(a dtauda(a))
   const double iadotoa = 1.0 / adotoa;
-  const double cothxor = 1.0 / tau;
   double dgrho = dgrho_matter;
   double z = 0, dz, clxr, qr, pir, clxg, qg, pig = 0, dgrhogal_t;
   if (e.no_nu) {
@@ -267,6 +421,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
       if (e.lmaxg > 2) {
         pigdot = denlk(e, 2) * qg - denlk2(e, 2) * y_g3 - opacity * (pig - polter) + 8.0 / 15.0 * k * sigma;
         AT(ayp, ix) = pigdot;
+#if !GC_EARLY_HIER
 #pragma unroll(kHierUnroll)
         for (int l = 3; l <= e.lmaxg - 1; l++) {
           ix = ix + 1;
@@ -274,6 +429,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
         }
         ix = ix + 1;
         AT(ayp, ix) = k * AT(ay, ix - 1) - (e.lmaxg + 1) * cothxor * AT(ay, ix) - opacity * AT(ay, ix);
+#endif
       } else {
         pigdot = denlk(e, 2) * qg - opacity * (pig - polter) + 8.0 / 15.0 * k * sigma;
         AT(ayp, ix) = pigdot;
@@ -281,6 +437,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
       ix = e.polind + 2;
       if (e.lmaxgpol > 2) {
         AT(ayp, ix) = -opacity * (y_e2 - polter) - k / 3.0 * y_e3;
+#if !GC_EARLY_HIER
 #pragma unroll(kHierUnroll)
         for (int l = 3; l <= e.lmaxgpol - 1; l++) {
           ix = ix + 1;
@@ -288,6 +445,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
         }
         ix = ix + 1;
         AT(ayp, ix) = -opacity * AT(ay, ix) + k * e.poltruncfac * AT(ay, ix - 1) - (e.lmaxgpol + 3) * cothxor * AT(ay, ix);
+#endif
       } else {
         AT(ayp, ix) = -opacity * (AT(ay, ix) - polter);
       }
@@ -310,6 +468,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
       int ix = e.r_ix + 2;
       if (e.lmaxnr > 2) {
         AT(ayp, ix) = denlk(e, 2) * qr - denlk2(e, 2) * y_r3 + 8.0 / 15.0 * k * sigma;
+#if !GC_EARLY_HIER
 #pragma unroll(kHierUnroll)
         for (int l = 3; l <= e.lmaxnr - 1; l++) {
           ix = ix + 1;
@@ -317,6 +476,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
         }
         ix = ix + 1;
         AT(ayp, ix) = k * AT(ay, ix - 1) - (e.lmaxnr + 1) * cothxor * AT(ay, ix);
+#endif
       } else {
         AT(ayp, ix) = denlk(e, 2) * qr + 8.0 / 15.0 * k * sigma;
       }
@@ -344,6 +504,34 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
       AT(ayp, o + 3) = (3 * w - 2) * adotoa * AT(ay, o + 3) + 2 * w * k * sigma - k / 5 * (3 * 1.0 * G30_t - 2 * G11_t);
     } else {
       int ind = e.nu_ix[nu_i];
+#if GC_EARLY_HIER
+      // l = 0 and l = 2 of every momentum bin (the other multipoles were formed ahead of the Einstein part): the loads of
+      // all bins first
+      const int lm = e.lmaxnu_tau[nu_i];
+      double y1[GC_MAX_NQ], y2[GC_MAX_NQ], y3[GC_MAX_NQ];
+#pragma unroll
+      for (int i = 0; i < GC_MAX_NQ; i++) {
+        const bool p = i < e.nq[nu_i];
+        const int b = ind + i * (lm + 1);
+        y1[i] = p ? AT(ay, b + 1) : 0.0;
+        y2[i] = (p && lm == 2) ? AT(ay, b + 2) : 0.0;
+        y3[i] = (p && lm != 2) ? AT(ay, b + 3) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < GC_MAX_NQ; i++) {
+        if (i < e.nq[nu_i]) {
+          const int b = ind + i * (lm + 1);
+          const double aq = a * M.nu_masses[nu_i] * M.inv_nu_q[i];
+          const double v = rsqrt(1.0 + aq * aq);
+          const double d0 = -k * (4.0 / 3.0 * z + v * y1[i]);
+          AT(ayp, b) = d0;
+          if (lm == 2)
+            AT(ayp, b + 2) = -d0 - 3 * cothxor * y2[i];
+          else
+            AT(ayp, b + 2) = v * (denlk(e, 2) * y1[i] - denlk2(e, 2) * y3[i]) + k * 8.0 / 15.0 * sigma;
+        }
+      }
+#else
       for (int i = 1; i <= e.nq[nu_i]; i++) {
         const double aq = a * M.nu_masses[nu_i] * M.inv_nu_q[i - 1];
         const double v = rsqrt(1.0 + aq * aq);
@@ -365,12 +553,35 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
         }
         ind = ind + 1;
       }
+#endif
     }
   }
   if (e.has_nu_rel) {
     int ind = e.nu_pert_ix;
     AT(ayp, ind) = +k * a2 * qr - k * AT(ay, ind + 1);
     int ind2 = e.r_ix;
+#if GC_EARLY_HIER
+    {  // l = 1 .. lmaxnu_pert: batches of 4 equations, their 2 x 6 loads first
+      const int lm = e.lmaxnu_pert;
+      for (int c = 0; c < lm; c += 4) {
+        double p[6], r[6];
+#pragma unroll
+        for (int u = 0; u < 6; u++) {
+          const bool in = c + u <= lm;  // the truncation equation reads nothing beyond its own element
+          p[u] = in ? AT(ay, ind + c + u) : 0.0;
+          r[u] = in ? AT(ay, ind2 + c + u) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int l = 1 + c + u;
+          if (l < lm)
+            AT(ayp, ind + l) = -a2 * (denlk(e, l) * r[u] - denlk2(e, l) * r[u + 2]) + (denlk(e, l) * p[u] - denlk2(e, l) * p[u + 2]);
+          else if (l == lm)
+            AT(ayp, ind + l) = k * (p[u] - a2 * r[u]) - (lm + 1) * cothxor * p[u + 1];
+        }
+      }
+    }
+#else
 #pragma unroll(kHierUnroll)
     for (int l = 1; l <= e.lmaxnu_pert - 1; l++) {
       ind = ind + 1;
@@ -381,6 +592,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
     ind = ind + 1;
     ind2 = ind2 + 1;
     AT(ayp, ind) = k * (AT(ay, ind - 1) - a2 * AT(ay, ind2 - 1)) - (e.lmaxnu_pert + 1) * cothxor * AT(ay, ind);
+#endif
   }
 }
 
@@ -470,6 +682,13 @@ struct Lane {
 // two 128-thread CTAs per SM need 2 x (128 x stride + 1 KB) <= 228 KB
 static_assert(GC_LANE_STRIDE <= 904, "Lane record too large for two CTAs per SM");
 
+// the lane's workspace base as a pointer the compiler knows to be global (it is read from a shared-memory record;
+// without the hint every access through it is a generic LD/ST)
+__device__ __forceinline__ double* ws_of(const Lane& L) {
+  double* q = L.ws;
+  __builtin_assume(__isGlobal(q));
+  return q;
+}
 // logical column c of the lane (0 = y, 1..8 = k1..k8, 9 = stage input / trial solution).  y and w9 trade places
 // when a trial step is accepted (L.ysel), so accepting a step costs no copy.
 __device__ __forceinline__ int phys_col(const Lane& L, int c) {
@@ -479,7 +698,9 @@ __device__ __forceinline__ int phys_col(const Lane& L, int c) {
 }
 __device__ __forceinline__ double* col(const Lane& L, int c) {
   const int p = phys_col(L, c);
-  return L.ws + (size_t)p * L.NV * GC_LANES;
+  double* q = L.ws + (size_t)p * L.NV * GC_LANES;
+  __builtin_assume(__isGlobal(q));  // the pointer comes out of a shared-memory record: without the hint every access is a generic LD/ST
+  return q;
 }
 
 // Verner 6(5) tableau of camb/subroutines.f90:930-1019 as rows over the derivative columns w1..w8:
@@ -520,20 +741,26 @@ __constant__ unsigned c_rowmask[8] = {0x01, 0x03, 0x07, 0x0f, 0x1f, 0x1f, 0x5f, 
 #define GC_LDK(fin, p) (*(p))
 #endif
 
+#if GC_STATE_CG
+#define GC_LDY(p) __ldcg(p)
+#else
+#define GC_LDY(p) (*(p))
+#endif
+
 template <int NC, int U, bool ROW0, bool FIN>
 __device__ __forceinline__ int combine_uniform(int i, int nend, const double* __restrict__ y, double* __restrict__ w9,
                                                const double* const* kc, const double* cf, const double* ce, double temp,
                                                bool stash, bool stash_k1, double* __restrict__ ys,
                                                double* __restrict__ ks, double& errn, double& ynew) {
-#pragma unroll(U == 4 ? 2 : 1)
-  for (; i + U - 1 <= nend; i += U) {
-    double yv[U], kv[NC][U];
+  auto load = [&](int i0, double (&yv)[U], double (&kv)[NC][U]) {
 #pragma unroll
-    for (int u = 0; u < U; u++) yv[u] = AT(y, i + u);
+    for (int u = 0; u < U; u++) yv[u] = GC_LDY(&AT(y, i0 + u));
 #pragma unroll
     for (int c = 0; c < NC; c++)
 #pragma unroll
-      for (int u = 0; u < U; u++) kv[c][u] = GC_LDK(FIN, &AT(kc[c], i + u));
+      for (int u = 0; u < U; u++) kv[c][u] = GC_LDK(FIN, &AT(kc[c], i0 + u));
+  };
+  auto comp = [&](int i0, const double (&yv)[U], const double (&kv)[NC][U]) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
       double v;
@@ -545,10 +772,10 @@ __device__ __forceinline__ int combine_uniform(int i, int nend, const double* __
         for (int c = 1; c < NC; c++) acc = acc + kv[c][u] * cf[c];
         v = yv[u] + temp * acc;
       }
-      AT(w9, i + u) = v;
+      AT(w9, i0 + u) = v;
       if (ROW0) {
-        if (stash) AT(ys, i + u) = yv[u];
-        if (stash_k1) AT(ks, i + u) = kv[0][u];
+        if (stash) AT(ys, i0 + u) = yv[u];
+        if (stash_k1) AT(ks, i0 + u) = kv[0][u];
       }
       if (FIN) {
         double a2 = kv[0][u] * ce[0];
@@ -559,8 +786,43 @@ __device__ __forceinline__ int combine_uniform(int i, int nend, const double* __
         ynew = fmax(ynew, fabs(v));
       }
     }
+  };
+#if GC_COMBINE_PIPE
+  // two batches in flight: the loads of the next batch are issued before the arithmetic and the stores of the current one,
+  // so the column stream never drains between batches (one exposed memory latency per pass instead of one per batch)
+  if (i + U - 1 > nend) return i;
+  double yA[U], kA[NC][U], yB[U], kB[NC][U];
+  load(i, yA, kA);
+  for (;;) {
+    const bool moreB = i + 2 * U - 1 <= nend;
+    if (moreB) load(i + U, yB, kB);
+    comp(i, yA, kA);
+    i += U;
+    if (!moreB) break;
+    const bool moreA = i + 2 * U - 1 <= nend;
+    if (moreA) load(i + U, yA, kA);
+    comp(i, yB, kB);
+    i += U;
+    if (!moreA) break;
   }
+#else
+#pragma unroll(U == 4 ? 2 : 1)
+  for (; i + U - 1 <= nend; i += U) {
+    double yv[U], kv[NC][U];
+    load(i, yv, kv);
+    comp(i, yv, kv);
+  }
+#endif
   return i;
+}
+
+// elements per batch of the uniform loops for a row that reads NC columns
+__host__ __device__ constexpr int combine_batch(int NC) {
+#if GC_COMBINE_PIPE
+  return NC <= 2 ? 8 : 4;
+#else
+  return NC >= 6 ? 4 : 8;
+#endif
 }
 
 // Row R of the tableau through combine_uniform: the compact column list of the row (ascending j, as the sums run) and its
@@ -571,7 +833,7 @@ __device__ __forceinline__ int combine_uniform_row(int i, int nend, const double
                                                    const double* const* kc, double temp, bool stash, bool stash_k1,
                                                    double* __restrict__ ys, double* __restrict__ ks, double& errn, double& ynew) {
   constexpr int NC = R == 0 ? 1 : R == 1 ? 2 : R == 2 ? 3 : R == 3 ? 4 : R <= 5 ? 5 : R == 6 ? 6 : 7;
-  constexpr int U = NC >= 6 ? 4 : 8;
+  constexpr int U = combine_batch(NC);
   const double* kk[NC];
   double cfk[NC], cek[NC];
 #pragma unroll
@@ -608,14 +870,17 @@ __device__ __forceinline__ void combine(Lane& L) {
   double* __restrict__ w9 = col(L, 9);
   const double* kc[8];
 #pragma unroll
-  for (int j = 0; j < 8; j++) kc[j] = L.ws + (size_t)(j + 1) * L.NV * GC_LANES;
+  for (int j = 0; j < 8; j++) kc[j] = ws_of(L) + (size_t)(j + 1) * L.NV * GC_LANES;
+#if GC_K8_IN_K2
+  kc[7] = kc[1];  // k8 lives in k2's column: row 6 is the last to read k2, row 7 the only one to read k8
+#endif
   const double temp = L.htrial / 1398169080000.0;
   double errn = 0.0, ynew = 0.0;
   // a lane whose last output is still pending keeps a copy of that y (this is the first pass over y since then)
   const bool stash = on && L.out_pending && !L.out_stashed;
-  double* __restrict__ ys = L.ws + (size_t)10 * L.NV * GC_LANES;
+  double* __restrict__ ys = ws_of(L) + (size_t)10 * L.NV * GC_LANES;
   const bool stash_k1 = stash && L.stash_k1;  // row 0 only: kv[0] is the k1 the output shares
-  double* __restrict__ ks = L.ws + (size_t)11 * L.NV * GC_LANES;
+  double* __restrict__ ks = ws_of(L) + (size_t)11 * L.NV * GC_LANES;
   // warp-uniform fast path: every lane forms the same row (the normal state of an aligned warp) -> no per-lane column
   // predicates; full batches below the shortest lane's length need no range predicates either
   const bool same_row = __all_sync(0xffffffffu, !on || cmask == umask);
@@ -635,7 +900,7 @@ __device__ __forceinline__ void combine(Lane& L) {
       }
     }
     {  // first element the uniform loops did not cover (same for every lane)
-      const int ub = (umask & 0xe0u) ? 4 : 8;
+      const int ub = combine_batch(__popc(umask));
       i = 1 + (nmin / ub) * ub;
     }
   }
@@ -647,7 +912,7 @@ __device__ __forceinline__ void combine(Lane& L) {
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         p[u] = i + u <= n;
-        yv[u] = p[u] ? AT(y, i + u) : 0.0;
+        yv[u] = p[u] ? GC_LDY(&AT(y, i + u)) : 0.0;
       }
 #pragma unroll
       for (int c = 0; c < 8; c++) {
@@ -723,8 +988,8 @@ __device__ __forceinline__ void combine_group(unsigned char* smem_base, int nown
   const double temp = O.htrial / 1398169080000.0;
   const bool stash = on && O.out_pending && !O.out_stashed;
   const bool stash_k1 = stash && O.stash_k1;
-  double* __restrict__ ys = O.ws + (size_t)10 * O.NV * GC_LANES;
-  double* __restrict__ ks = O.ws + (size_t)11 * O.NV * GC_LANES;
+  double* __restrict__ ys = ws_of(O) + (size_t)10 * O.NV * GC_LANES;
+  double* __restrict__ ks = ws_of(O) + (size_t)11 * O.NV * GC_LANES;
   const int nmax = __reduce_max_sync(0xffffffffu, n);
   double errn = 0.0, ynew = 0.0;
   for (int i0 = 1 + sub; i0 <= nmax; i0 += 4 * gsz) {
@@ -733,12 +998,12 @@ __device__ __forceinline__ void combine_group(unsigned char* smem_base, int nown
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       p[u] = i0 + u * gsz <= n;
-      yv[u] = p[u] ? AT(y, i0 + u * gsz) : 0.0;
+      yv[u] = p[u] ? GC_LDY(&AT(y, i0 + u * gsz)) : 0.0;
     }
 #pragma unroll
     for (int c = 0; c < 8; c++) {
       const bool mine = (cmask >> c) & 1u;
-      const double* kcol = O.ws + (size_t)(c + 1) * O.NV * GC_LANES;
+      const double* kcol = ws_of(O) + (size_t)((GC_K8_IN_K2 && c == 7) ? 2 : c + 1) * O.NV * GC_LANES;
 #pragma unroll
       for (int u = 0; u < 4; u++) kv[c][u] = (mine && p[u]) ? GC_LDK(false, &AT(kcol, i0 + u * gsz)) : 0.0;
     }
@@ -1155,7 +1420,7 @@ __device__ __forceinline__ void advance(Lane& L, int wphase, bool align) {
           else
             L.req_tau = x + L.htrial * frac;
           L.req_in = 9;
-          L.req_out = s + 1;
+          L.req_out = (GC_K8_IN_K2 && s == 7) ? 2 : s + 1;
           L.want_derivs = true;
           L.stage = s + 1;
           return;

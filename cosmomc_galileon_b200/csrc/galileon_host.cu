@@ -27,6 +27,18 @@ struct Background {
   void nu_pressures(double a, double* rhonu, double* pnu) const {
     for (int i = 0; i < M.n_eig; i++) gc::Nu_background(M, a * M.nu_masses[i], rhonu[i], pnu[i]);
   }
+  // the pressure alone (same branches and arithmetic as Nu_background, camb/modules.f90:1721-1754, without the density's
+  // exponential): all the right-hand side and the stability conditions read
+  double nu_pressure(double am) const {
+    if (am <= GC_AM_MINP) return (2 - (1.0 + GC_NU_CONST2 * am * am)) / 3.0;
+    if (am >= GC_AM_MAXP) return 900.0 / 120.0 / GC_NU_CONST * (GC_ZETA5 - 63.0 / 4 * GC_ZETA7 / (am * am)) / am;
+    double d = std::log(am * 100.0) * M.inv_dlnam + 1.0;
+    const int i = (int)d;
+    d = d - i;
+    const double* r0 = M.nu_tab + (size_t)(i - 1) * 6;
+    const double* r1 = r0 + 6;
+    return std::exp(gc::herm(r0[2], r0[3], r1[2], r1[3], d));
+  }
   void rhs(double a, const double y[3], double f[3]) const;
   int stability(double a, const double y[3]);
   void evolve_apply(double& t, double t1, double& h, double y[3]) const;
@@ -57,9 +69,7 @@ void Background::rhs(double a, const double y[3], double f[3]) const {
   const double sigma = 2.0 * h + 2.0 * c3 * prod3 - 15.0 * c4 * h * prod4 + 21.0 * c5 * h2 * prod5 + 6.0 * cG * h * prod2;
   double lambda = 3.0 * h2 + orad / (a2 * a2) + c2 / 2.0 * prod2 - 2.0 * c3 * h * prod3 + 7.5 * c4 * h2 * prod4 -
                   9.0 * c5 * h3 * prod5 - cG * h2 * prod2;
-  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
-  nu_pressures(a, rhonu, pnu);
-  for (int i = 0; i < M.n_eig; i++) lambda += M.grhormass[i] * pnu[i] / (a2 * a2 * h0 * h0);
+  for (int i = 0; i < M.n_eig; i++) lambda += M.grhormass[i] * nu_pressure(a * M.nu_masses[i]) / (a2 * a2 * h0 * h0);
   const double omega = 2 * c3 * h2 * prod2 - 12 * c4 * h3 * prod3 + 15 * c5 * h4 * prod4 + 4.0 * cG * h3 * prod;
   const double denom = sigma * beta - alpha * omega;
   f[0] = (omega * gamma - lambda * beta) / (a * denom);
@@ -83,9 +93,7 @@ int Background::stability(double a, const double y[3]) {
                   9.0 * c5 * h3 * prod5 - cG * h2 * prod2;
   const double omega = 2 * c3 * h2 * prod2 - 12 * c4 * h3 * prod3 + 15 * c5 * h4 * prod4 + 4.0 * cG * h3 * prod;
   const double denom = sigma * beta - alpha * omega;
-  double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
-  nu_pressures(a, rhonu, pnu);
-  for (int i = 0; i < M.n_eig; i++) lambda += M.grhormass[i] * pnu[i] / (a * a * a * a * h0 * h0);
+  for (int i = 0; i < M.n_eig; i++) lambda += M.grhormass[i] * nu_pressure(a * M.nu_masses[i]) / (a * a * a * a * h0 * h0);
   const double dhdlna = (omega * gamma - lambda * beta) / denom;
   const double dxdlna = (alpha * lambda - sigma * gamma) / denom - xgal;
   const double k1 = -6 * c4 * h * prod2 * (dhdlna * xgal + h * dxdlna + prod / 3.0) +
@@ -233,10 +241,15 @@ int Background::run(double om, bool reject_negative_density, std::vector<double>
                     std::vector<double>& xg) {
   const double amin = 1e-10, amax = 1.;
   const double q = std::pow(amin / amax, 1. / NB);
-  grid.resize(NB + 1);
+  // the node positions do not depend on the model: computed once per process
+  static const std::vector<double> nodes = [&] {
+    std::vector<double> g(NB + 1);
+    for (int i = 0; i <= NB; i++) g[i] = amax * std::pow(q, i);
+    return g;
+  }();
+  grid = nodes;
   hub.assign(NB + 1, 0.0);
   xg.assign(NB + 1, 0.0);
-  for (int i = 0; i <= NB; i++) grid[i] = amax * std::pow(q, i);
   double y[3] = {1.0, 1.0, 0.0};
   double a = 1, h = -1e-6;
   double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
