@@ -62,6 +62,15 @@ constexpr int kHierUnroll = GC_HIER_UNROLL;
 #ifndef GC_COMBINE_PIPE
 #define GC_COMBINE_PIPE 0
 #endif
+#ifndef GC_COMBINE_NC4
+#define GC_COMBINE_NC4 6  // rows reading at least this many columns use batches of 4 elements instead of 8
+#endif
+#ifndef GC_PIPE_MIN_NC
+#define GC_PIPE_MIN_NC 1
+#endif
+#ifndef GC_PIPE_MAX_NC
+#define GC_PIPE_MAX_NC 7
+#endif
 
 namespace gc {
 
@@ -85,20 +94,31 @@ struct InCol {
 // The last equation of a run is the truncation formula, which does not read y(ix+1): that element is not loaded.
 // skip_l: a multipole whose equation the caller evaluates elsewhere (nothing is stored for it).
 #ifndef GC_HIER_BATCH
-#define GC_HIER_BATCH 8
+#define GC_HIER_BATCH 6
 #endif
+// the two halves of a batch: the U + 2 loads of batch c (c = 0, U, 2U ...) of a run, and its U equations
+template <int U>
+__device__ __forceinline__ void hier_load(const InCol ay, int ix0, int cnt, int c, double (&v)[U + 2]) {
+#pragma unroll
+  for (int u = 0; u < U + 2; u++) v[u] = (c < cnt && c + u <= cnt) ? AT(ay, ix0 + c + u - 1) : 0.0;
+}
+template <int U, class F>
+__device__ __forceinline__ void hier_eval(double* __restrict__ ayp, int ix0, int l0, int cnt, int c, int skip_l,
+                                          const double (&v)[U + 2], F f) {
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const int l = l0 + c + u;
+    if (c + u < cnt && l != skip_l) AT(ayp, ix0 + c + u) = f(l, v[u], v[u + 1], v[u + 2]);
+  }
+}
+// batches c0, c0 + U, ... of a run, one after the other
 template <class F>
-__device__ __forceinline__ void hier_run(const InCol ay, double* __restrict__ ayp, int ix0, int l0, int cnt, int skip_l, F f) {
+__device__ __forceinline__ void hier_run(const InCol ay, double* __restrict__ ayp, int ix0, int l0, int cnt, int skip_l, int c0, F f) {
   constexpr int U = GC_HIER_BATCH;
-  for (int c = 0; c < cnt; c += U) {
+  for (int c = c0; c < cnt; c += U) {
     double v[U + 2];
-#pragma unroll
-    for (int u = 0; u < U + 2; u++) v[u] = (c + u <= cnt) ? AT(ay, ix0 + c + u - 1) : 0.0;
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const int l = l0 + c + u;
-      if (c + u < cnt && l != skip_l) AT(ayp, ix0 + c + u) = f(l, v[u], v[u + 1], v[u + 2]);
-    }
+    hier_load<U>(ay, ix0, cnt, c, v);
+    hier_eval<U>(ayp, ix0, l0, cnt, c, skip_l, v, f);
   }
 }
 
@@ -201,26 +221,25 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
   // and tau: they are evaluated HERE, before the Einstein / Galileon part, while few registers are live -- whole runs of
   // multipoles per exposed memory latency instead of a latency per statement under the register pressure further down.
   // Every expression is the one of camb/equations_galileon.f90:2437-2589; the stores go to distinct elements of y'.
-  if (!e.no_phot && !e.TightCoupling) {
-    if (e.lmaxg > 2) {
-      const int lm = e.lmaxg;
-      hier_run(ay, ayp, e.g_ix + 3, 3, lm - 2, -1, [&](int l, double ym, double y0, double yp) {
-        return l < lm ? (denlk(e, l) * ym - denlk2(e, l) * yp) - opacity * y0 : k * ym - (lm + 1) * cothxor * y0 - opacity * y0;
-      });
-    }
-    if (e.lmaxgpol > 2) {
-      const int lm = e.lmaxgpol;
-      hier_run(ay, ayp, e.polind + 3, 3, lm - 2, -1, [&](int l, double ym, double y0, double yp) {
-        return l < lm ? -opacity * y0 + (denlk(e, l) * ym - polfack(e, l) * yp)
-                      : -opacity * y0 + k * e.poltruncfac * ym - (lm + 3) * cothxor * y0;
-      });
-    }
-  }
-  if (!e.no_nu && !e.high_ktau && e.lmaxnr > 2) {
-    const int lm = e.lmaxnr;
-    hier_run(ay, ayp, e.r_ix + 3, 3, lm - 2, -1, [&](int l, double ym, double y0, double yp) {
-      return l < lm ? (denlk(e, l) * ym - denlk2(e, l) * yp) : k * ym - (lm + 1) * cothxor * y0;
-    });
+  {
+    const bool hp = !e.no_phot && !e.TightCoupling;
+    const int lmg = e.lmaxg, lme = e.lmaxgpol, lmr = e.lmaxnr;
+    const int ng = (hp && lmg > 2) ? lmg - 2 : 0, ne = (hp && lme > 2) ? lme - 2 : 0;
+    const int nr = (!e.no_nu && !e.high_ktau && lmr > 2) ? lmr - 2 : 0;
+    auto fg = [&](int l, double ym, double y0, double yp) {
+      return l < lmg ? (denlk(e, l) * ym - denlk2(e, l) * yp) - opacity * y0 : k * ym - (lmg + 1) * cothxor * y0 - opacity * y0;
+    };
+    auto fe = [&](int l, double ym, double y0, double yp) {
+      return l < lme ? -opacity * y0 + (denlk(e, l) * ym - polfack(e, l) * yp)
+                     : -opacity * y0 + k * e.poltruncfac * ym - (lme + 3) * cothxor * y0;
+    };
+    auto fr = [&](int l, double ym, double y0, double yp) {
+      return l < lmr ? (denlk(e, l) * ym - denlk2(e, l) * yp) : k * ym - (lmr + 1) * cothxor * y0;
+    };
+    // one hierarchy after the other (issuing the first batches of all of them together measured 12 % SLOWER)
+    hier_run(ay, ayp, e.g_ix + 3, 3, ng, -1, 0, fg);
+    hier_run(ay, ayp, e.polind + 3, 3, ne, -1, 0, fe);
+    hier_run(ay, ayp, e.r_ix + 3, 3, nr, -1, 0, fr);
   }
   if (M.Num_Nu_massive != 0) {
     for (int nu_i = 0; nu_i < M.n_eig; nu_i++) {
@@ -231,7 +250,7 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
         const double aq = a * M.nu_masses[nu_i] * M.inv_nu_q[i - 1];
         const double v = rsqrt(1.0 + aq * aq);
         // l = 1 .. lm of this momentum bin; l = 0 and l = 2 need z and sigma and follow below.  With lm = 2 only l = 1.
-        hier_run(ay, ayp, ind + 1, 1, lm == 2 ? 1 : lm, 2, [&](int l, double ym, double y0, double yp) {
+        hier_run(ay, ayp, ind + 1, 1, lm == 2 ? 1 : lm, 2, 0, [&](int l, double ym, double y0, double yp) {
           return (l < lm || lm == 2) ? v * (denlk(e, l) * ym - denlk2(e, l) * yp) : k * v * ym - (lm + 1) * cothxor * y0;
         });
         ind = ind + lm + 1;
@@ -788,40 +807,43 @@ __device__ __forceinline__ int combine_uniform(int i, int nend, const double* __
     }
   };
 #if GC_COMBINE_PIPE
-  // two batches in flight: the loads of the next batch are issued before the arithmetic and the stores of the current one,
-  // so the column stream never drains between batches (one exposed memory latency per pass instead of one per batch)
-  if (i + U - 1 > nend) return i;
-  double yA[U], kA[NC][U], yB[U], kB[NC][U];
-  load(i, yA, kA);
-  for (;;) {
-    const bool moreB = i + 2 * U - 1 <= nend;
-    if (moreB) load(i + U, yB, kB);
-    comp(i, yA, kA);
-    i += U;
-    if (!moreB) break;
-    const bool moreA = i + 2 * U - 1 <= nend;
-    if (moreA) load(i + U, yA, kA);
-    comp(i, yB, kB);
-    i += U;
-    if (!moreA) break;
+  if (NC >= GC_PIPE_MIN_NC && NC <= GC_PIPE_MAX_NC) {
+    // two batches in flight: the loads of the next batch are issued before the arithmetic and the stores of the current
+    // one, so the column stream never drains between batches (one exposed memory latency per pass, not one per batch)
+    if (i + U - 1 > nend) return i;
+    double yc[U], kcur[NC][U];
+    load(i, yc, kcur);
+    for (; i + 2 * U - 1 <= nend; i += U) {
+      double yn[U], kn[NC][U];
+      load(i + U, yn, kn);
+      comp(i, yc, kcur);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        yc[u] = yn[u];
+#pragma unroll
+        for (int c = 0; c < NC; c++) kcur[c][u] = kn[c][u];
+      }
+    }
+    comp(i, yc, kcur);
+    return i + U;
   }
-#else
+#endif
 #pragma unroll(U == 4 ? 2 : 1)
   for (; i + U - 1 <= nend; i += U) {
     double yv[U], kv[NC][U];
     load(i, yv, kv);
     comp(i, yv, kv);
   }
-#endif
   return i;
 }
 
 // elements per batch of the uniform loops for a row that reads NC columns
 __host__ __device__ constexpr int combine_batch(int NC) {
 #if GC_COMBINE_PIPE
-  return NC <= 2 ? 8 : 4;
-#else
+  if (NC >= GC_PIPE_MIN_NC && NC <= GC_PIPE_MAX_NC) return NC <= 2 ? 8 : NC <= 5 ? 4 : 2;
   return NC >= 6 ? 4 : 8;
+#else
+  return NC >= GC_COMBINE_NC4 ? 4 : 8;
 #endif
 }
 
@@ -1761,11 +1783,16 @@ extern "C" cudaError_t GC_ENTRY(gc_launch_evolve_batch)(const DevModel* models, 
     const char* e = getenv("GALCAMB_LATENCY_ITEMS");  // experiment knob: item count up to which one-warp CTAs are used
     lat_items = e ? atol(e) : 160000;  // measured crossover with the lock-step shape: ~800 models
   }
+  static long smem_pad = -1;
+  if (smem_pad < 0) {
+    const char* e = getenv("GALCAMB_EVOLVE_SMEM_PAD");  // experiment knob: unused shared memory per CTA (limits the CTAs per SM)
+    smem_pad = e ? atol(e) : 0;
+  }
   const int threads = nitems <= lat_items ? 32 : GC_EVOLVE_THREADS;
-  const size_t smem = (size_t)threads * GC_LANE_STRIDE;  // lane records
+  const size_t smem = (size_t)threads * GC_LANE_STRIDE + (threads > 32 ? (size_t)smem_pad : 0);  // lane records
   {  // per device and cheap: set on every launch (several devices may be driven from one process)
     cudaError_t e = cudaFuncSetAttribute(gc::evolve_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((size_t)GC_EVOLVE_THREADS * GC_LANE_STRIDE));
+                                         (int)((size_t)GC_EVOLVE_THREADS * GC_LANE_STRIDE + (size_t)smem_pad));
     if (e != cudaSuccess) return e;
   }
   const int blocks = (nitems + threads - 1) / threads;

@@ -825,57 +825,71 @@ int Model::recombination() {
     const double zp1 = 1.0 + z, zp13 = zp1 * zp1 * zp1;
     const double n = Nnow * zp13, n_He = fHe * Nnow * zp13, Trad = Tnow * zp1;
     const double Hz = 1 / dtauda(1 / zp1) * (zp1 * zp1) / MPC_in_sec;
-    const double Rdown = 1.e-19 * a_PPB * std::pow(Tmat / 1.e4, b_PPB) / (1.0 + c_PPB * std::pow(Tmat / 1.e4, d_PPB));
-    const double Rup = Rdown * std::pow(R.CR * Tmat, 1.5) * std::exp(-R.CDB / Tmat);
-    const double sq_0 = std::sqrt(Tmat / T_0), sq_1 = std::sqrt(Tmat / T_1);
-    double Rdown_He = a_VF / (sq_0 * std::pow(1.0 + sq_0, 1.0 - b_VF));
-    Rdown_He = Rdown_He / std::pow(1.0 + sq_1, 1.0 + b_VF);
-    double Rup_He = Rdown_He * std::pow(R.CR * Tmat, 1.5) * std::exp(-R.CDB_He / Tmat);
-    Rup_He = 4.0 * Rup_He;
-    const double He_Boltz = (R.Bfact / Tmat) > 680.0 ? std::exp(680.0) : std::exp(R.Bfact / Tmat);
-    double K;
-    if (!Hswitch) {
-      K = R.CK / Hz;
-    } else {
-      const double g1 = (std::log(zp1) - zGauss1) / wGauss1, g2 = (std::log(zp1) - zGauss2) / wGauss2;
-      K = R.CK / Hz * (1.0 + AGauss1 * std::exp(-(g1 * g1)) + AGauss2 * std::exp(-(g2 * g2)));
-    }
-    double Rdown_trip = a_trip / (sq_0 * std::pow(1.0 + sq_0, 1.0 - b_trip));
-    Rdown_trip = Rdown_trip / std::pow(1.0 + sq_1, 1.0 + b_trip);
-    double Rup_trip = Rdown_trip * std::exp(-h_P * C * L_He2St_ion / (k_B * Tmat));
-    Rup_trip = Rup_trip * std::pow(R.CR * Tmat, 1.5) * (4.0 / 3.0);
-    const int Heflag = ((x_He < 5.e-9) || (x_He > 0.98)) ? 0 : Heswitch;
-    double K_He, CfHe_t = 0;
-    if (Heflag == 0) {
-      K_He = R.CK_He / Hz;
-    } else {
-      const double tauHe_s = A2P_s * R.CK_He * 3.0 * n_He * (1.0 - x_He) / Hz;
-      const double pHe_s = (1.0 - std::exp(-tauHe_s)) / tauHe_s;
-      K_He = 1.0 / (A2P_s * pHe_s * 3.0 * n_He * (1.0 - x_He));
-      if (((Heflag == 2) || (Heflag >= 5)) && x_H < 0.9999999) {
-        double Doppler = 2.0 * k_B * Tmat / (m_H * not4 * C * C);
-        Doppler = C * L_He_2p * std::sqrt(Doppler);
-        const double gamma_2Ps = 3.0 * A2P_s * fHe * (1.0 - x_He) * C * C /
-                                 (std::sqrt(Pi) * sigma_He_2Ps * 8.0 * Pi * Doppler * (1.0 - x_H)) / ((C * L_He_2p) * (C * L_He_2p));
-        const double AHcon = A2P_s / (1.0 + 0.36 * std::pow(gamma_2Ps, fudge_He));
-        K_He = 1.0 / ((A2P_s * pHe_s + AHcon) * 3.0 * n_He * (1.0 - x_He));
-      }
-      if (Heflag >= 3) {
-        double tauHe_t = A2P_t * n_He * (1.0 - x_He) * 3.0;
-        tauHe_t = tauHe_t / (8.0 * Pi * Hz * (L_He_2Pt * L_He_2Pt * L_He_2Pt));
-        const double pHe_t = (1.0 - std::exp(-tauHe_t)) / tauHe_t;
-        const double CL_PSt = h_P * C * (L_He_2Pt - L_He_2St) / k_B;
-        if ((Heflag == 3) || (Heflag == 5) || (x_H > 0.99999)) {
-          CfHe_t = A2P_t * pHe_t * std::exp(-CL_PSt / Tmat);
-          CfHe_t = CfHe_t / (Rup_trip + CfHe_t);
+    // Only the terms an equation reads are formed: y'(x_H) is zero above x_H = 0.99 and the helium equation is zero below
+    // x_He = 1e-15 (camb/recfast.f90:1039-1073), so the hydrogen rates are skipped during helium recombination and the
+    // helium rates afterwards -- same expressions, same results, about half of the transcendental calls.
+    const bool needH = !(x_H > SP(0.99)), needHe = !(x_He < SP(1.e-15));
+    const double crt15 = (needH || needHe) ? std::pow(R.CR * Tmat, 1.5) : 0.0;
+    double Rdown = 0, Rup = 0, K = 0;
+    if (needH) {
+      Rdown = 1.e-19 * a_PPB * std::pow(Tmat / 1.e4, b_PPB) / (1.0 + c_PPB * std::pow(Tmat / 1.e4, d_PPB));
+      Rup = Rdown * crt15 * std::exp(-R.CDB / Tmat);
+      if (!(x_H > 0.985)) {
+        if (!Hswitch) {
+          K = R.CK / Hz;
         } else {
+          const double lz = std::log(zp1);
+          const double g1 = (lz - zGauss1) / wGauss1, g2 = (lz - zGauss2) / wGauss2;
+          K = R.CK / Hz * (1.0 + AGauss1 * std::exp(-(g1 * g1)) + AGauss2 * std::exp(-(g2 * g2)));
+        }
+      }
+    }
+    double Rdown_He = 0, Rup_He = 0, He_Boltz = 0, Rdown_trip = 0, Rup_trip = 0, K_He = 0, CfHe_t = 0;
+    const int Heflag = ((x_He < 5.e-9) || (x_He > 0.98)) ? 0 : Heswitch;
+    if (needHe) {
+      const double sq_0 = std::sqrt(Tmat / T_0), sq_1 = std::sqrt(Tmat / T_1);
+      Rdown_He = a_VF / (sq_0 * std::pow(1.0 + sq_0, 1.0 - b_VF));
+      Rdown_He = Rdown_He / std::pow(1.0 + sq_1, 1.0 + b_VF);
+      Rup_He = Rdown_He * crt15 * std::exp(-R.CDB_He / Tmat);
+      Rup_He = 4.0 * Rup_He;
+      He_Boltz = (R.Bfact / Tmat) > 680.0 ? std::exp(680.0) : std::exp(R.Bfact / Tmat);
+      if (Heflag >= 3) {  // the triplet rates are read only then (:1004-1030, :1068-1073)
+        Rdown_trip = a_trip / (sq_0 * std::pow(1.0 + sq_0, 1.0 - b_trip));
+        Rdown_trip = Rdown_trip / std::pow(1.0 + sq_1, 1.0 + b_trip);
+        Rup_trip = Rdown_trip * std::exp(-h_P * C * L_He2St_ion / (k_B * Tmat));
+        Rup_trip = Rup_trip * crt15 * (4.0 / 3.0);
+      }
+      if (Heflag == 0) {
+        K_He = R.CK_He / Hz;
+      } else {
+        const double tauHe_s = A2P_s * R.CK_He * 3.0 * n_He * (1.0 - x_He) / Hz;
+        const double pHe_s = (1.0 - std::exp(-tauHe_s)) / tauHe_s;
+        K_He = 1.0 / (A2P_s * pHe_s * 3.0 * n_He * (1.0 - x_He));
+        if (((Heflag == 2) || (Heflag >= 5)) && x_H < 0.9999999) {
           double Doppler = 2.0 * k_B * Tmat / (m_H * not4 * C * C);
-          Doppler = C * L_He_2Pt * std::sqrt(Doppler);
-          const double gamma_2Pt = 3.0 * A2P_t * fHe * (1.0 - x_He) * C * C /
-                                   (std::sqrt(Pi) * sigma_He_2Pt * 8.0 * Pi * Doppler * (1.0 - x_H)) / ((C * L_He_2Pt) * (C * L_He_2Pt));
-          const double AHcon = A2P_t / (1.0 + 0.66 * std::pow(gamma_2Pt, 0.9)) / 3.0;
-          CfHe_t = (A2P_t * pHe_t + AHcon) * std::exp(-CL_PSt / Tmat);
-          CfHe_t = CfHe_t / (Rup_trip + CfHe_t);
+          Doppler = C * L_He_2p * std::sqrt(Doppler);
+          const double gamma_2Ps = 3.0 * A2P_s * fHe * (1.0 - x_He) * C * C /
+                                   (std::sqrt(Pi) * sigma_He_2Ps * 8.0 * Pi * Doppler * (1.0 - x_H)) / ((C * L_He_2p) * (C * L_He_2p));
+          const double AHcon = A2P_s / (1.0 + 0.36 * std::pow(gamma_2Ps, fudge_He));
+          K_He = 1.0 / ((A2P_s * pHe_s + AHcon) * 3.0 * n_He * (1.0 - x_He));
+        }
+        if (Heflag >= 3) {
+          double tauHe_t = A2P_t * n_He * (1.0 - x_He) * 3.0;
+          tauHe_t = tauHe_t / (8.0 * Pi * Hz * (L_He_2Pt * L_He_2Pt * L_He_2Pt));
+          const double pHe_t = (1.0 - std::exp(-tauHe_t)) / tauHe_t;
+          const double CL_PSt = h_P * C * (L_He_2Pt - L_He_2St) / k_B;
+          if ((Heflag == 3) || (Heflag == 5) || (x_H > 0.99999)) {
+            CfHe_t = A2P_t * pHe_t * std::exp(-CL_PSt / Tmat);
+            CfHe_t = CfHe_t / (Rup_trip + CfHe_t);
+          } else {
+            double Doppler = 2.0 * k_B * Tmat / (m_H * not4 * C * C);
+            Doppler = C * L_He_2Pt * std::sqrt(Doppler);
+            const double gamma_2Pt = 3.0 * A2P_t * fHe * (1.0 - x_He) * C * C /
+                                     (std::sqrt(Pi) * sigma_He_2Pt * 8.0 * Pi * Doppler * (1.0 - x_H)) / ((C * L_He_2Pt) * (C * L_He_2Pt));
+            const double AHcon = A2P_t / (1.0 + 0.66 * std::pow(gamma_2Pt, 0.9)) / 3.0;
+            CfHe_t = (A2P_t * pHe_t + AHcon) * std::exp(-CL_PSt / Tmat);
+            CfHe_t = CfHe_t / (Rup_trip + CfHe_t);
+          }
         }
       }
     }
