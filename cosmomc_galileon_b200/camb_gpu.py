@@ -244,6 +244,7 @@ def load_library():
         L.galcamb_prestaged_upload_.argtypes = []
         L.galcamb_set_host_threads_.argtypes = [C.POINTER(_I)]
         L.galcamb_set_host_threads_.restype = None
+        L.galcamb_set_prestage_device_.argtypes = [C.POINTER(_I)]
         L.galcamb_select_device_.argtypes = [C.POINTER(_I)]
         L.galcamb_multi_params_to_cls_.argtypes = [C.POINTER(_I), C.POINTER(CParams), C.POINTER(_I), C.POINTER(_I), C.c_void_p]
         L.galcamb_multi_single_cls_.argtypes = [C.POINTER(_I), C.POINTER(CParams), C.c_void_p, C.c_void_p]
@@ -505,6 +506,10 @@ class GalCamb:
 
     def set_host_threads(self, n):
         self.L.galcamb_set_host_threads_(C.byref(_I(int(n))))
+
+    def set_prestage_device(self, device):
+        """Galileon backgrounds of a batch on this device (-1: on the host threads); galcamb_set_prestage_device_."""
+        self.L.galcamb_set_prestage_device_(C.byref(_I(int(device))))
 
     # the same with the lensing post-step: (Cl[n,3,lmax-1], Cl_lensed[n,4,lmax_lensed-1])
     def batch_lensed_cls(self, models):

@@ -623,13 +623,13 @@ int galcamb_evolve_sources_(void) {
   //    sets the run time (single spectra, MCMC chain steps, k-sharded calls);
   //  * one lane per item, state in a lane-interleaved L2/HBM workspace (csrc/evolve_batch.cu): 256 items per SM and
   //    every lane busy in the scalar part of the right-hand side -- the choice for large parameter batches.
-  // Measured crossover on config 2: ~100 models (20 000 items; 48 models 1.12 s vs 128 models 1.81 s).
+  // Measured crossover on config 2: ~64 models (13 000 items; 32 models 0.88 s vs 1.54 s, 64: 1.63 vs 1.64, 96: 2.45 vs 1.73).
   long total_items = 0;
   for (auto& s : g.slots) total_items += (s.host.nk + s.host.nk_tr + g.kshard_world - 1) / g.kshard_world;
   static long octet_items = -1;
   if (octet_items < 0) {
     const char* e = getenv("GALCAMB_OCTET_ITEMS");  // experiment knob: item count up to which the eight-lane form is used
-    octet_items = e ? atol(e) : 20000;
+    octet_items = e ? atol(e) : 13000;
   }
   const int NVP = NV;
   bool want_tr = false;

@@ -617,13 +617,14 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
 
 }  // namespace gc
 
-// batch mode: 4 warps per CTA, 2 CTAs per SM (255 registers, 113 KB of lane records each); the warps of a CTA run
-// derivs() in lock-step (see the main loop)
+// batch mode: ONE CTA of 7 warps per SM (255 registers, 170-194 KB of lane records); its warps run derivs() in lock-step
+// (see the main loop), so an SM fetches one instruction stream.  Measured on 1024 distinct points (evolve ms): 2 CTAs x 4
+// warps 5026, 2 x 3: 5597, 1 x 4: 6691, 1 x 6: 5220, 1 x 7: 4744, 1 x 8: 4811, 3 x 4 (168 registers): 6607, 4 x 4 (128): 9468.
 #ifndef GC_EVOLVE_THREADS
-#define GC_EVOLVE_THREADS 128
+#define GC_EVOLVE_THREADS 224
 #endif
 #ifndef GC_EVOLVE_MINBLOCKS
-#define GC_EVOLVE_MINBLOCKS 2
+#define GC_EVOLVE_MINBLOCKS 1
 #endif
 
 namespace gc {
@@ -698,8 +699,8 @@ struct Lane {
 // element i of column c of this lane: ws[(c*NV + i-1)*32]  (ws already points at the lane's slot)
 // shared-memory stride between the Lane records of consecutive threads: sizeof(Lane) rounded up to an odd multiple of 8
 #define GC_LANE_STRIDE ((((sizeof(gc::Lane) + 7) / 8) | 1) * 8)
-// two 128-thread CTAs per SM need 2 x (128 x stride + 1 KB) <= 228 KB
-static_assert(GC_LANE_STRIDE <= 904, "Lane record too large for two CTAs per SM");
+// the CTA's lane records + 1 KB must fit the 227 KB of dynamic shared memory of an SM
+static_assert((size_t)GC_EVOLVE_THREADS * GC_LANE_STRIDE + 1024 <= 227 * 1024, "Lane records too large for the SM");
 
 // the lane's workspace base as a pointer the compiler knows to be global (it is read from a shared-memory record;
 // without the hint every access through it is a generic LD/ST)
@@ -1776,19 +1777,30 @@ extern "C" void GC_ENTRY(gc_upload_constants_batch)() {
 
 extern "C" cudaError_t GC_ENTRY(gc_launch_evolve_batch)(const DevModel* models, const int2* items, int nitems, double* workspace, int NV,
                                               int* status, unsigned long long* counters, cudaStream_t stream) {
-  // Mid-size batches (up to ~800 models = 25 warps per k index): one warp per CTA, so that no warp waits for another at
-  // the lock-step barrier; larger batches: 4-warp CTAs in lock step (instruction-cache sharing, see the main loop).
+  // CTA size: as many warps as it takes to give every SM one CTA, up to the 7 of a full batch.  The warps of a CTA run
+  // derivs() in lock step (one instruction stream per SM, see the main loop); with fewer warps than SMs every warp is its
+  // own CTA.  Measured (evolve ms, distinct points, one-warp CTAs -> this rule): 128 models 1988 -> 1852, 256: 2826 -> 1922,
+  // 512: 5101 -> 3148.
   static long lat_items = -1;
   if (lat_items < 0) {
     const char* e = getenv("GALCAMB_LATENCY_ITEMS");  // experiment knob: item count up to which one-warp CTAs are used
-    lat_items = e ? atol(e) : 160000;  // measured crossover with the lock-step shape: ~800 models
+    lat_items = e ? atol(e) : 0;
   }
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+  }
+  const int nwarps = (nitems + 31) / 32;
+  int cta_warps = (nwarps + n_sm - 1) / n_sm;
+  cta_warps = cta_warps < 1 ? 1 : cta_warps > GC_EVOLVE_THREADS / 32 ? GC_EVOLVE_THREADS / 32 : cta_warps;
   static long smem_pad = -1;
   if (smem_pad < 0) {
     const char* e = getenv("GALCAMB_EVOLVE_SMEM_PAD");  // experiment knob: unused shared memory per CTA (limits the CTAs per SM)
     smem_pad = e ? atol(e) : 0;
   }
-  const int threads = nitems <= lat_items ? 32 : GC_EVOLVE_THREADS;
+  const int threads = nitems <= lat_items ? 32 : 32 * cta_warps;
   const size_t smem = (size_t)threads * GC_LANE_STRIDE + (threads > 32 ? (size_t)smem_pad : 0);  // lane records
   {  // per device and cheap: set on every launch (several devices may be driven from one process)
     cudaError_t e = cudaFuncSetAttribute(gc::evolve_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

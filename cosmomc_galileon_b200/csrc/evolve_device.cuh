@@ -134,7 +134,8 @@ __device__ inline double Thermo_OpacityToTime(const DevModel& M, double opacity)
 
 // nu_tab rows: {r1, dr1, p1, dp1, ddr1, ddp1}
 // camb/modules.f90:1721-1754
-GC_HOSTDEV inline void Nu_background(const DevModel& M, double am, double& rhonu, double& pnu) {
+template <class ModelT>
+GC_HOSTDEV inline void Nu_background(const ModelT& M, double am, double& rhonu, double& pnu) {
   if (am <= GC_AM_MINP) {
     rhonu = 1.0 + GC_NU_CONST2 * am * am;
     pnu = (2 - rhonu) / 3.0;
@@ -166,7 +167,8 @@ GC_HOSTDEV inline double Nu_drho(const DevModel& M, double am, double adotoa, do
 }
 
 // camb/modules.f90:1821-1850
-GC_HOSTDEV inline double Nu_dp(const DevModel& M, double am, double adotoa, double pnu) {
+template <class ModelT>
+GC_HOSTDEV inline double Nu_dp(const ModelT& M, double am, double adotoa, double pnu) {
   if (am < GC_AM_MINP) return 2 * adotoa * (1.0 - GC_NU_CONST2 * am * am) / 3.0 - 4.0 / 3.0 * adotoa;
   if (am > GC_AM_MAXP)
     return -900.0 / 120.0 / GC_NU_CONST * (GC_ZETA5 - 189.0 / 4 * GC_ZETA7 / (am * am)) * adotoa / am;

@@ -21,27 +21,39 @@ namespace {
 using gc::Nu_background;
 
 // one background problem: the constants of the ODE + the memory of the two "no sudden jump" stability tests
+// what the background problem reads of a model (the field names of DevModel, so that the neutrino look-ups of
+// evolve_device.cuh take either): small enough to stay in registers when the integrator runs as a device lane
+struct BgModel {
+  double c2, c3, c4, c5, cG, h0, orad;
+  double dlnam, inv_dlnam;
+  double grhormass[GC_MAX_NU], nu_masses[GC_MAX_NU];
+  const double* nu_tab;  // [n][6] rows {r1, dr1, p1, dp1, ddr1, ddp1}; host or device memory
+  int n_eig;
+};
+
 struct Background {
-  DevModel M{};  // constants c2..c5, cG, h0, orad, n_eig, grhormass, nu_masses, nu table pointer (host memory here)
+  BgModel M{};
   double noghost_previous = 0, cs2_previous = 0;
-  void nu_pressures(double a, double* rhonu, double* pnu) const {
+  GC_HOSTDEV void nu_pressures(double a, double* rhonu, double* pnu) const {
     for (int i = 0; i < M.n_eig; i++) gc::Nu_background(M, a * M.nu_masses[i], rhonu[i], pnu[i]);
   }
   // the pressure alone (same branches and arithmetic as Nu_background, camb/modules.f90:1721-1754, without the density's
   // exponential): all the right-hand side and the stability conditions read
-  double nu_pressure(double am) const {
+  GC_HOSTDEV double nu_pressure(double am) const {
     if (am <= GC_AM_MINP) return (2 - (1.0 + GC_NU_CONST2 * am * am)) / 3.0;
     if (am >= GC_AM_MAXP) return 900.0 / 120.0 / GC_NU_CONST * (GC_ZETA5 - 63.0 / 4 * GC_ZETA7 / (am * am)) / am;
-    double d = std::log(am * 100.0) * M.inv_dlnam + 1.0;
+    double d = log(am * 100.0) * M.inv_dlnam + 1.0;
     const int i = (int)d;
     d = d - i;
     const double* r0 = M.nu_tab + (size_t)(i - 1) * 6;
     const double* r1 = r0 + 6;
-    return std::exp(gc::herm(r0[2], r0[3], r1[2], r1[3], d));
+    return exp(gc::herm(r0[2], r0[3], r1[2], r1[3], d));
   }
-  void rhs(double a, const double y[3], double f[3]) const;
-  int stability(double a, const double y[3]);
-  void evolve_apply(double& t, double t1, double& h, double y[3]) const;
+  GC_HOSTDEV void rhs(double a, const double y[3], double f[3]) const;
+  GC_HOSTDEV int stability(double a, const double y[3]);
+  GC_HOSTDEV void evolve_apply(double& t, double t1, double& h, double y[3]) const;
+  // the node loop of calcHubbleGalileon on given node positions; hub / xg = NB + 1 values, element i at [i * stride]
+  GC_HOSTDEV int run_nodes(double om, bool reject_negative_density, const double* grid, double* hub, double* xg, long stride);
   int run(double om, bool reject_negative_density, std::vector<double>& grid, std::vector<double>& hub, std::vector<double>& xg);
 };
 
@@ -58,7 +70,7 @@ constexpr int NB = 29999;  // camb/galileon.cc:72 (30 000 nodes)
 void nu_pressures(double a, double* rhonu, double* pnu) { G.nu_pressures(a, rhonu, pnu); }
 
 // d(hbar, dpi/da, pi)/da, camb/galileon.cc:254-302
-void Background::rhs(double a, const double y[3], double f[3]) const {
+GC_HOSTDEV void Background::rhs(double a, const double y[3], double f[3]) const {
   const double c2 = M.c2, c3 = M.c3, c4 = M.c4, c5 = M.c5, cG = M.cG, h0 = M.h0, orad = M.orad;
   const double prod = a * y[0] * y[1];
   const double prod2 = prod * prod, prod3 = prod * prod2, prod4 = prod * prod3, prod5 = prod * prod4;
@@ -79,7 +91,7 @@ void Background::rhs(double a, const double y[3], double f[3]) const {
 
 // ghost / Laplace stability of scalar and tensor perturbations at one node, camb/galileon.cc:130-245
 // returns 0 or the number of the failed condition (1 no-ghost, 2 c_s^2, 3 tensor no-ghost, 4 c_T^2)
-int Background::stability(double a, const double y[3]) {
+GC_HOSTDEV int Background::stability(double a, const double y[3]) {
   const double c2 = M.c2, c3 = M.c3, c4 = M.c4, c5 = M.c5, cG = M.cG, h0 = M.h0, orad = M.orad;
   const double xgal = a * y[1];
   const double prod = xgal * y[0];
@@ -119,9 +131,9 @@ int Background::stability(double a, const double y[3]) {
   if (cs2 < 0) return 2;
   if (noghostt < 0) return 3;
   if (ct2 < 0) return 4;
-  if (noghost > -1.0 && noghost < -1e-8 && std::fabs((noghost - noghost_previous) / noghost) > 0.25) return 1;
+  if (noghost > -1.0 && noghost < -1e-8 && fabs((noghost - noghost_previous) / noghost) > 0.25) return 1;
   noghost_previous = noghost;
-  if (std::fabs((cs2 - cs2_previous) / cs2_previous) > 1) return 2;
+  if (fabs((cs2 - cs2_previous) / cs2_previous) > 1) return 2;
   cs2_previous = cs2;
   return 0;
 }
@@ -131,22 +143,24 @@ int Background::stability(double a, const double y[3]) {
 // it, so it is not computed: one right-hand side in seven less, bit-identical results.)
 struct Rkf45 {
   const Background& B;
-  void step(double t, double h, double y[3], double yerr[3], const double k1[3]) const {
-    static const double c[] = {1.0 / 4.0, 3.0 / 8.0, 12.0 / 13.0, 1.0, 1.0 / 2.0};
-    static const double a2[] = {1.0 / 4.0};
-    static const double a3[] = {3.0 / 32.0, 9.0 / 32.0};
-    static const double a4[] = {1932.0 / 2197.0, -7200.0 / 2197.0, 7296.0 / 2197.0};
-    static const double a5[] = {8341.0 / 4104.0, -32832.0 / 4104.0, 29440.0 / 4104.0, -845.0 / 4104.0};
-    static const double a6[] = {-6080.0 / 20520.0, 41040.0 / 20520.0, -28352.0 / 20520.0, 9295.0 / 20520.0, -5643.0 / 20520.0};
-    static const double b[] = {902880.0 / 7618050.0, 0.0, 3953664.0 / 7618050.0, 3855735.0 / 7618050.0, -1371249.0 / 7618050.0,
-                               277020.0 / 7618050.0};
-    static const double e[] = {1.0 / 360.0, 0.0, -128.0 / 4275.0, -2197.0 / 75240.0, 1.0 / 50.0, 2.0 / 55.0};
+  GC_HOSTDEV void step(double t, double h, double y[3], double yerr[3], const double k1[3]) const {
+    const double c[] = {1.0 / 4.0, 3.0 / 8.0, 12.0 / 13.0, 1.0, 1.0 / 2.0};
+    // rows of the tableau (row s - 1 = the coefficients of stage s + 1, padded with zeros that are never read)
+    const double rows[5][5] = {{1.0 / 4.0, 0, 0, 0, 0},
+                               {3.0 / 32.0, 9.0 / 32.0, 0, 0, 0},
+                               {1932.0 / 2197.0, -7200.0 / 2197.0, 7296.0 / 2197.0, 0, 0},
+                               {8341.0 / 4104.0, -32832.0 / 4104.0, 29440.0 / 4104.0, -845.0 / 4104.0, 0},
+                               {-6080.0 / 20520.0, 41040.0 / 20520.0, -28352.0 / 20520.0, 9295.0 / 20520.0, -5643.0 / 20520.0}};
+    const double b[] = {902880.0 / 7618050.0, 0.0, 3953664.0 / 7618050.0, 3855735.0 / 7618050.0, -1371249.0 / 7618050.0,
+                        277020.0 / 7618050.0};
+    const double e[] = {1.0 / 360.0, 0.0, -128.0 / 4275.0, -2197.0 / 75240.0, 1.0 / 50.0, 2.0 / 55.0};
     double k[6][3], yt[3];
     for (int i = 0; i < 3; i++) k[0][i] = k1[i];
-    const double* const rows[] = {a2, a3, a4, a5, a6};
+#pragma unroll
     for (int s = 1; s < 6; s++) {
       for (int i = 0; i < 3; i++) {
         double acc = rows[s - 1][0] * k[0][i];
+#pragma unroll
         for (int j = 1; j < s; j++) acc += rows[s - 1][j] * k[j][i];
         yt[i] = y[i] + (s == 1 ? rows[0][0] * h * k[0][i] : h * acc);
       }
@@ -162,7 +176,7 @@ struct Rkf45 {
 };
 
 // one accepted step towards t1 with the standard y-error controller (eps_abs 1e-18, eps_rel 1e-16, a_y = 1, a_dydt = 0)
-void Background::evolve_apply(double& t, double t1, double& h, double y[3]) const {
+GC_HOSTDEV void Background::evolve_apply(double& t, double t1, double& h, double y[3]) const {
   const double eps_abs = 1e-18, eps_rel = 1e-16, S = 0.9, ord = 5.0;
   const Rkf45 stepper{*this};
   const double t0 = t, dt = t1 - t0;
@@ -177,16 +191,16 @@ void Background::evolve_apply(double& t, double t1, double& h, double y[3]) cons
     t = final_step ? t1 : t0 + h0;
     const double h_old = h0;
     double rmax = 2.2250738585072014e-308;
-    for (int i = 0; i < 3; i++) rmax = std::fmax(rmax, std::fabs(yerr[i]) / std::fabs(eps_rel * std::fabs(y[i]) + eps_abs));
+    for (int i = 0; i < 3; i++) rmax = fmax(rmax, fabs(yerr[i]) / fabs(eps_rel * fabs(y[i]) + eps_abs));
     if (rmax > 1.1) {  // shrink and retry from (t0, y0) unless the step cannot shrink any more
-      h0 = h_old * std::fmax(0.2, S / std::pow(rmax, 1.0 / ord));
-      if (std::fabs(h0) < std::fabs(h_old) && t + h0 != t) {
+      h0 = h_old * fmax(0.2, S / pow(rmax, 1.0 / ord));
+      if (fabs(h0) < fabs(h_old) && t + h0 != t) {
         for (int i = 0; i < 3; i++) y[i] = y0[i];
         continue;
       }
       h0 = h_old;
     } else if (rmax < 0.5) {
-      h0 = h_old * std::fmin(5.0, std::fmax(1.0, S / std::pow(rmax, 1.0 / (ord + 1.0))));
+      h0 = h_old * fmin(5.0, fmax(1.0, S / pow(rmax, 1.0 / (ord + 1.0))));
     }
     break;
   }
@@ -235,27 +249,14 @@ double spline_eval(const std::vector<double>& xa, const std::vector<double>& ya,
   return ya[lo] + delx * (b_i + delx * (c[lo] + delx * d_i));
 }
 
-// calcHubbleGalileon, camb/galileon.cc:332-438 (= calcHubble, camb/theta.cc:179-295, which also rejects a negative
-// Galileon density): from a = 1 (hbar = 1, dpi/da = 1) down to 1e-10 on NB + 1 log-spaced nodes, every node checked
-int Background::run(double om, bool reject_negative_density, std::vector<double>& grid, std::vector<double>& hub,
-                    std::vector<double>& xg) {
-  const double amin = 1e-10, amax = 1.;
-  const double q = std::pow(amin / amax, 1. / NB);
-  // the node positions do not depend on the model: computed once per process
-  static const std::vector<double> nodes = [&] {
-    std::vector<double> g(NB + 1);
-    for (int i = 0; i <= NB; i++) g[i] = amax * std::pow(q, i);
-    return g;
-  }();
-  grid = nodes;
-  hub.assign(NB + 1, 0.0);
-  xg.assign(NB + 1, 0.0);
+GC_HOSTDEV int Background::run_nodes(double om, bool reject_negative_density, const double* grid, double* hub, double* xg,
+                                     long stride) {
   double y[3] = {1.0, 1.0, 0.0};
   double a = 1, h = -1e-6;
   double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
   for (int i = 0; i <= NB; ++i) {
     while (a > grid[i]) evolve_apply(a, grid[i], h, y);
-    if (std::isnan(y[0]) || std::isnan(y[1]) || std::isnan(y[2])) return 8;
+    if (isnan(y[0]) || isnan(y[1]) || isnan(y[2])) return 8;
     if (stability(a, y)) return 7;
     const double h2 = y[0] * y[0];
     const double x1 = a * y[1], x2 = x1 * x1, x3 = x2 * x1, a3 = a * a * a;
@@ -266,16 +267,38 @@ int Background::run(double om, bool reject_negative_density, std::vector<double>
     for (int j = 0; j < M.n_eig; j++) OmegaM -= M.grhormass[j] * rhonu[j] / (a3 * a * 3. * h2 * (M.h0 * M.h0));
     const double OmTest = om / (a3 * h2);
     if (reject_negative_density && OmegaP < 0) return 5;                  // camb/theta.cc:263
-    if (std::fabs((OmegaM - OmTest) / OmTest) > 1e-4) return 4;           // Friedmann closure, camb/galileon.cc:420
-    hub[i] = y[0];
-    xg[i] = y[1];
+    if (fabs((OmegaM - OmTest) / OmTest) > 1e-4) return 4;                // Friedmann closure, camb/galileon.cc:420
+    hub[i * stride] = y[0];
+    xg[i * stride] = y[1];
   }
   return 0;
 }
 
+// the node positions (amax q^i, i = 0 .. NB) do not depend on the model: computed once per process
+static const std::vector<double>& background_nodes() {
+  static const std::vector<double> nodes = [] {
+    const double amin = 1e-10, amax = 1.;
+    const double q = std::pow(amin / amax, 1. / NB);
+    std::vector<double> g(NB + 1);
+    for (int i = 0; i <= NB; i++) g[i] = amax * std::pow(q, i);
+    return g;
+  }();
+  return nodes;
+}
+
+// calcHubbleGalileon, camb/galileon.cc:332-438 (= calcHubble, camb/theta.cc:179-295, which also rejects a negative
+// Galileon density): from a = 1 (hbar = 1, dpi/da = 1) down to 1e-10 on NB + 1 log-spaced nodes, every node checked
+int Background::run(double om, bool reject_negative_density, std::vector<double>& grid, std::vector<double>& hub,
+                    std::vector<double>& xg) {
+  grid = background_nodes();
+  hub.assign(NB + 1, 0.0);
+  xg.assign(NB + 1, 0.0);
+  return run_nodes(om, reject_negative_density, grid.data(), hub.data(), xg.data(), 1);
+}
+
 // flatness closure: the highest non-zero coefficient follows from the others (camb/galileon.cc:520-575)
-static void close_coefficients(Background& B, double om, double c3in, double c4in) {
-  DevModel& M = B.M;
+GC_HOSTDEV static void close_coefficients(Background& B, double om, double c3in, double c4in) {
+  BgModel& M = B.M;
   const int neig = M.n_eig;
   const double grhom = 3 * (M.h0 * M.h0);
   double rhonu[GC_MAX_NU], pnu[GC_MAX_NU];
@@ -373,7 +396,7 @@ int galileon_set_nu_tables_(const double* r1, const double* p1, const double* dr
 int arrays_(double* omegar, double* omegam, double* H0in, double* c2in, double* c3in, double* c4in, double* cGin,
             double* grhormass, double* nu_masses, int* nu_mass_eigenstates) {
   G.ready = false;
-  DevModel& M = G.M;
+  BgModel& M = G.M;
   const int neig = *nu_mass_eigenstates;
   if (neig < 0 || neig > GC_MAX_NU) return 5;
   if (neig > 0 && G.nu_tab.empty()) return 5;  // galileon_set_nu_tables_ first
@@ -407,7 +430,7 @@ int gc_galileon_background(double omegar, double omegam, double h0, double c2, d
                            std::vector<double>& a, std::vector<double>& h, std::vector<double>& x) {
   if (neig < 0 || neig > GC_MAX_NU) return 5;
   Background B;
-  DevModel& M = B.M;
+  BgModel& M = B.M;
   M.n_eig = neig;
   for (int i = 0; i < neig; i++) {
     M.grhormass[i] = grhormass[i];
@@ -440,7 +463,7 @@ double theta_(double* omegam, double* orad, double* ombh2, double* h0, double* a
   if (neig < 0 || neig > GC_MAX_NU || (neig > 0 && G.nu_tab.empty())) return -1;
   const double cl = 2.99792458e8;
   Background B;
-  DevModel& M = B.M;
+  BgModel& M = B.M;
   M.nu_tab = G.M.nu_tab;
   M.dlnam = G.M.dlnam;
   M.inv_dlnam = G.M.inv_dlnam;
@@ -610,3 +633,131 @@ double pigalprime_(double* point, double* hcamb, double* xcamb, double* dhcamb, 
 }
 
 }  // extern "C"
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// The same background integration for a whole batch of cosmologies on the device: one lane per cosmology (the node loop
+// is sequential: 30 000 Fehlberg steps, each depending on the one before), every lane running Background::run_nodes --
+// the code above, compiled for the device without FMA contraction (this file is built -fmad=false), on the node positions
+// computed by the host.  What can differ from the host run is the last bit of log / exp / pow (the neutrino pressure
+// look-up and the step-size controller); tests/test_gpu_parity.py::test_device_background_against_host bounds it.
+// The launch needs one warp slot and 8 K registers per 32 cosmologies and no shared memory, so it runs NEXT TO the
+// per-k kernel of the previous batch (which leaves exactly that much of an SM free) on its own stream.
+struct GcBackgroundIn {  // inputs of arrays_ (camb/galileon.cc:503-519) for one cosmology
+  double omegar, omegam, h0, c2, c3in, c4in, cG;
+  int neig;
+  double grhormass[GC_MAX_NU], nu_masses[GC_MAX_NU];
+};
+
+namespace {
+
+__global__ void __launch_bounds__(32) gal_background_kernel(const GcBackgroundIn* __restrict__ in, int n, const double* __restrict__ nu_tab,
+                                                            double dlnam, const double* __restrict__ nodes, double* __restrict__ h,
+                                                            double* __restrict__ x, double* __restrict__ coef, int* __restrict__ status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const GcBackgroundIn I = in[i];
+  if (I.neig < 0 || I.neig > GC_MAX_NU) {
+    status[i] = 5;
+    return;
+  }
+  Background B;
+  BgModel& M = B.M;
+  M.n_eig = I.neig;
+  for (int j = 0; j < I.neig; j++) {
+    M.grhormass[j] = I.grhormass[j];
+    M.nu_masses[j] = I.nu_masses[j];
+  }
+  M.nu_tab = nu_tab;
+  M.dlnam = dlnam;
+  M.inv_dlnam = 1.0 / dlnam;
+  M.orad = I.omegar;
+  M.h0 = I.h0;
+  M.c2 = I.c2;
+  M.cG = I.cG;
+  M.c3 = M.c4 = M.c5 = 0;
+  close_coefficients(B, I.omegam, I.c3in, I.c4in);
+  // ascending a: node j of the descending integration grid is element NB - j of the model's table (NB + 2 per model)
+  double* hm = h + (size_t)i * (NB + 2) + NB;
+  double* xm = x + (size_t)i * (NB + 2) + NB;
+  status[i] = B.run_nodes(I.omegam, false, nodes, hm, xm, -1);
+  coef[i * 5 + 0] = M.c2; coef[i * 5 + 1] = M.c3; coef[i * 5 + 2] = M.c4; coef[i * 5 + 3] = M.c5; coef[i * 5 + 4] = M.cG;
+}
+
+struct DeviceBackground {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  GcBackgroundIn* d_in = nullptr;
+  double *d_nu = nullptr, *d_nodes = nullptr, *d_h = nullptr, *d_x = nullptr, *d_coef = nullptr;
+  int* d_status = nullptr;
+  double *p_h = nullptr, *p_x = nullptr;  // pinned
+  size_t cap = 0;
+  size_t nu_rows = 0;
+};
+DeviceBackground DB;
+
+}  // namespace
+
+// n cosmologies at once on `device`.  h_out / x_out: per model NB + 2 ascending values (the extrapolated node beyond a = 1
+// included, like gc_galileon_background); a_out: the NB + 2 abscissae (the same for every model); coef_out [n][5];
+// status_out [n] as arrays_.  Returns 0 or a CUDA failure as 100.
+int gc_galileon_background_device(int device, const GcBackgroundIn* in, int n, const double* nu_tab, size_t nu_rows, double dlnam,
+                                  std::vector<double>& a_out, const double** h_out, const double** x_out, double* coef_out,
+                                  int* status_out) {
+#define GCB(call)                        \
+  do {                                   \
+    if ((call) != cudaSuccess) return 100; \
+  } while (0)
+  GCB(cudaSetDevice(device));
+  const std::vector<double>& nodes = background_nodes();
+  if (DB.device != device) {
+    if (DB.device >= 0) return 100;  // one device per process for this path
+    GCB(cudaStreamCreateWithFlags(&DB.stream, cudaStreamNonBlocking));
+    GCB(cudaMalloc(&DB.d_nodes, nodes.size() * sizeof(double)));
+    GCB(cudaMemcpyAsync(DB.d_nodes, nodes.data(), nodes.size() * sizeof(double), cudaMemcpyHostToDevice, DB.stream));
+    DB.device = device;
+  }
+  if (nu_rows > 0 && DB.nu_rows != nu_rows) {
+    if (DB.d_nu) cudaFree(DB.d_nu);
+    GCB(cudaMalloc(&DB.d_nu, nu_rows * 6 * sizeof(double)));
+    GCB(cudaMemcpyAsync(DB.d_nu, nu_tab, nu_rows * 6 * sizeof(double), cudaMemcpyHostToDevice, DB.stream));
+    DB.nu_rows = nu_rows;
+  }
+  if ((size_t)n > DB.cap) {
+    if (DB.d_in) { cudaFree(DB.d_in); cudaFree(DB.d_h); cudaFree(DB.d_x); cudaFree(DB.d_coef); cudaFree(DB.d_status); cudaFreeHost(DB.p_h); cudaFreeHost(DB.p_x); }
+    const size_t per = (size_t)(NB + 2);
+    GCB(cudaMalloc(&DB.d_in, n * sizeof(GcBackgroundIn)));
+    GCB(cudaMalloc(&DB.d_h, n * per * sizeof(double)));
+    GCB(cudaMalloc(&DB.d_x, n * per * sizeof(double)));
+    GCB(cudaMalloc(&DB.d_coef, (size_t)n * 5 * sizeof(double)));
+    GCB(cudaMalloc(&DB.d_status, n * sizeof(int)));
+    GCB(cudaMallocHost(&DB.p_h, n * per * sizeof(double)));
+    GCB(cudaMallocHost(&DB.p_x, n * per * sizeof(double)));
+    DB.cap = n;
+  }
+  const size_t per = (size_t)(NB + 2);
+  GCB(cudaMemcpyAsync(DB.d_in, in, n * sizeof(GcBackgroundIn), cudaMemcpyHostToDevice, DB.stream));
+  gal_background_kernel<<<(n + 31) / 32, 32, 0, DB.stream>>>(DB.d_in, n, DB.d_nu, dlnam, DB.d_nodes, DB.d_h, DB.d_x, DB.d_coef, DB.d_status);
+  GCB(cudaGetLastError());
+  GCB(cudaMemcpyAsync(DB.p_h, DB.d_h, n * per * sizeof(double), cudaMemcpyDeviceToHost, DB.stream));
+  GCB(cudaMemcpyAsync(DB.p_x, DB.d_x, n * per * sizeof(double), cudaMemcpyDeviceToHost, DB.stream));
+  GCB(cudaMemcpyAsync(coef_out, DB.d_coef, (size_t)n * 5 * sizeof(double), cudaMemcpyDeviceToHost, DB.stream));
+  GCB(cudaMemcpyAsync(status_out, DB.d_status, n * sizeof(int), cudaMemcpyDeviceToHost, DB.stream));
+  GCB(cudaStreamSynchronize(DB.stream));
+#undef GCB
+  // abscissae and the linearly extrapolated node beyond a = 1 (camb/galileon.cc:655-663), as ascending_tables()
+  a_out.assign(NB + 2, 0.0);
+  for (int i = 0; i <= NB; i++) a_out[i] = nodes[NB - i];
+  const double q = std::pow(1e-10 / 1., 1. / NB);
+  a_out[NB + 1] = 1. / q;
+  for (int m = 0; m < n; m++) {
+    if (status_out[m]) continue;
+    double* h = DB.p_h + (size_t)m * per;
+    double* x = DB.p_x + (size_t)m * per;
+    h[NB + 1] = (h[NB] - h[NB - 1]) / (a_out[NB] - a_out[NB - 1]) * (a_out[NB + 1] - a_out[NB - 1]) + h[NB - 1];
+    x[NB + 1] = (x[NB] - x[NB - 1]) / (a_out[NB] - a_out[NB - 1]) * (a_out[NB + 1] - a_out[NB - 1]) + x[NB - 1];
+  }
+  *h_out = DB.p_h;
+  *x_out = DB.p_x;
+  return 0;
+}

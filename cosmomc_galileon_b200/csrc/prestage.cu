@@ -27,10 +27,20 @@
 
 #include "../../include/galcamb.h"
 #include "pack.h"
+#include "model.h"
 
 int gc_galileon_background(double omegar, double omegam, double h0, double c2, double c3in, double c4in, double cG, int neig,
                            const double* grhormass, const double* nu_masses, const double* nu_tab, double dlnam, double* coef,
                            std::vector<double>& a, std::vector<double>& h, std::vector<double>& x);
+
+struct GcBackgroundIn {  // csrc/galileon_host.cu
+  double omegar, omegam, h0, c2, c3in, c4in, cG;
+  int neig;
+  double grhormass[GC_MAX_NU], nu_masses[GC_MAX_NU];
+};
+int gc_galileon_background_device(int device, const GcBackgroundIn* in, int n, const double* nu_tab, size_t nu_rows, double dlnam,
+                                  std::vector<double>& a_out, const double** h_out, const double** x_out, double* coef_out,
+                                  int* status_out);
 
 namespace pre {
 
@@ -522,6 +532,9 @@ struct Model {
   // matter transfer functions: output times (ascending) and the wavenumbers beyond the source grid
   std::vector<double> tautf, k_transfer;
   double prof_bg_ms = 0, prof_rec_ms = 0;  // GALCAMB_PRESTAGE_PROFILE
+  // Galileon background of a batch integrated on the device (prestage_into): 0 = integrate here on the host, 1 = stop in
+  // params_set() once the inputs of the background are known, 2 = gal_a / gal_h / gal_x / gal_coef / bg_status are given
+  int bg_mode = 0, bg_status = 0;
   // the tables in the device layout (csrc/pack.h), packed by the pre-stage thread that built the point
   std::vector<double> packed;
   gcpack::Info pinfo;
@@ -667,10 +680,12 @@ int Model::params_set() {
     const double omegar = (grhog + grhornomass) / grhom, omegam = P.omegab + P.omegac, hub = P.H0 / c * 1000;
     gal_h0 = hub;
     gal_orad = omegar;
+    if (bg_mode == 1) return 0;
     const auto tb0 = std::chrono::steady_clock::now();
-    const int st = gc_galileon_background(omegar, omegam, hub, P.c2, P.c3, P.c4, P.cG, Nu_mass_eigenstates, grhormass + 1,
-                                          nu_masses + 1, g_nu.rows.empty() ? nullptr : g_nu.rows.data(), g_nu.dlnam, gal_coef, gal_a,
-                                          gal_h, gal_x);
+    const int st = bg_mode == 2 ? bg_status
+                                : gc_galileon_background(omegar, omegam, hub, P.c2, P.c3, P.c4, P.cG, Nu_mass_eigenstates, grhormass + 1,
+                                                         nu_masses + 1, g_nu.rows.empty() ? nullptr : g_nu.rows.data(), g_nu.dlnam,
+                                                         gal_coef, gal_a, gal_h, gal_x);
     prof_bg_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count();
     if (st != 0) return fail(6, "Didn't compute background successfully");
     // natural-spline coefficients of hbar (c = y''/2, gsl_interp_cspline): spline_natural gives y''
@@ -1340,6 +1355,8 @@ static std::vector<galcamb_params> g_async_params;
 static std::thread g_async;
 static int g_async_rc = 0;
 static int g_host_threads = 0;
+static int g_bg_device = -1;  // galcamb_set_prestage_device_: device that integrates the Galileon backgrounds of a batch (-1: host)
+static std::mutex g_bg_mutex;
 // cs2 table address of every point of the current batch -> its index (galcamb_model views carry no back pointer)
 static std::unordered_map<const double*, int> g_by_table;
 static void index_current_batch() {
@@ -1436,6 +1453,55 @@ static int prestage_into(std::vector<pre::Model>& batch, std::string& err, const
   for (int i = 0; i < n; i++) batch[i].P = params[i];
   int nt = nthreads > 0 ? nthreads : g_host_threads > 0 ? g_host_threads : (int)std::thread::hardware_concurrency();
   nt = std::max(1, std::min(nt, n));
+  // Galileon backgrounds of the whole batch in one device launch (csrc/galileon_host.cu), next to whatever the device is
+  // running for the previous batch; the host threads below then start from the finished tables.
+  if (g_bg_device >= 0 && n > 1) {
+    std::vector<GcBackgroundIn> in;
+    std::vector<int> who;
+    for (int i = 0; i < n; i++) {
+      Model& M = batch[i];
+      if (!M.P.use_galileon) continue;
+      M.bg_mode = 1;
+      const int rc = M.params_set();  // up to the inputs of the background
+      M.bg_mode = 0;
+      if (rc != 0) continue;          // the full run below reports the error
+      GcBackgroundIn b{};
+      b.omegar = M.gal_orad;
+      b.omegam = M.P.omegab + M.P.omegac;
+      b.h0 = M.gal_h0;
+      b.c2 = M.P.c2; b.c3in = M.P.c3; b.c4in = M.P.c4; b.cG = M.P.cG;
+      b.neig = M.Nu_mass_eigenstates;
+      if (b.neig > GC_MAX_NU) continue;
+      for (int j = 0; j < b.neig; j++) {
+        b.grhormass[j] = M.grhormass[j + 1];
+        b.nu_masses[j] = M.nu_masses[j + 1];
+      }
+      in.push_back(b);
+      who.push_back(i);
+    }
+    if (!in.empty()) {
+      std::lock_guard<std::mutex> lock(g_bg_mutex);
+      std::vector<double> a, coef(in.size() * 5);
+      std::vector<int> st(in.size());
+      const double *h = nullptr, *x = nullptr;
+      const int rc = gc_galileon_background_device(g_bg_device, in.data(), (int)in.size(), g_nu.rows.empty() ? nullptr : g_nu.rows.data(),
+                                                   g_nu.rows.size() / 6, g_nu.dlnam, a, &h, &x, coef.data(), st.data());
+      if (rc == 0) {
+        const size_t per = a.size();
+        for (size_t m = 0; m < who.size(); m++) {
+          Model& M = batch[who[m]];
+          M.bg_mode = 2;
+          M.bg_status = st[m];
+          if (st[m] == 0) {
+            M.gal_a = a;
+            M.gal_h.assign(h + m * per, h + (m + 1) * per);
+            M.gal_x.assign(x + m * per, x + (m + 1) * per);
+            for (int c = 0; c < 5; c++) M.gal_coef[c] = coef[m * 5 + c];
+          }
+        }
+      }  // on a CUDA failure the host threads integrate as usual
+    }
+  }
   // the shared neutrino tables are built by whichever thread gets there first (std::call_once)
   std::atomic<int> next{0};
   auto work = [&]() {
@@ -1521,6 +1587,12 @@ int galcamb_prestage_count_(void) { return (int)pre::g_batch.size(); }
 // host threads the library may use for the pre-stage and for packing model tables (0 = all cores): with one process per
 // GPU on a shared host each rank passes cores / ranks
 void galcamb_set_host_threads_(const int* n) { pre::g_host_threads = *n; }
+// device >= 0: the Galileon backgrounds of a batch are integrated on that device (one lane per cosmology, one launch per
+// batch, next to the per-k kernel of the previous batch); -1 (default): on the host threads
+int galcamb_set_prestage_device_(const int* device) {
+  pre::g_bg_device = *device;
+  return 0;
+}
 int galcamb_get_host_threads_(void) { return pre::g_host_threads; }
 
 int galcamb_prestage_status_(const int* i, int* status) {

@@ -223,6 +223,10 @@ int galcamb_prestaged_upload_(void); /* current pre-staged batch -> device slots
 /* host threads the library may use (pre-stage, table packing); 0 = all cores.  One process per GPU: cores / ranks. */
 void galcamb_set_host_threads_(const int* n);
 int galcamb_get_host_threads_(void);
+/* Where the Galileon background integrations of a batch run (arrays_, camb/galileon.cc:503-688): device >= 0 -- one lane
+ * per cosmology in one launch per batch, next to the per-k kernel of the previous batch; -1 (default) -- on the host
+ * threads.  Batches of one point always take the host path. */
+int galcamb_set_prestage_device_(const int* device);
 /* parameters -> C_l in one call: pre-stage on the host threads, stages 1-4 on the device.  Points the pre-stage or the
  * integration rejects come back as NaN rows; Cl_out as in galcamb_batch_cls_. */
 int galcamb_params_to_cls_(const galcamb_params* params, const int* n, const int* nthreads, double* Cl_out);

@@ -434,6 +434,43 @@ def test_parameters_to_cls_without_the_oracle_in_the_loop(gpu):
         assert np.max(np.abs(out[i] / o.Cl() - 1)) < TOL_CL, i
 
 
+def test_device_background_against_host(gpu):
+    """galcamb_set_prestage_device_: the Galileon backgrounds of a batch integrated on the device (one lane per cosmology,
+    csrc/galileon_host.cu) against the same integrator on the host threads -- same tables (1e-12; the last bit of
+    log / exp / pow is all that differs), same rejections, same C_l."""
+    from cosmomc_galileon_b200 import make_params, prestage
+    lmax = 800
+    pts = [GAL, dict(GAL, c2=+5.0), dict(GAL, ombh2=0.0225, omch2=0.1160), LCDM, dict(GAL, H0=76.5, c3=-3.2),
+           dict(GAL, omnuh2=0.0)]
+    params = [make_params(Max_l=lmax, Max_eta_k=2.0 * lmax, **P) for P in pts]
+    th, sh = prestage(params, nthreads=2, copy=True)
+    cl_h = gpu.params_to_cls(params)
+    gpu.set_prestage_device(0)
+    try:
+        td, sd = prestage(params, nthreads=2, copy=True)
+        cl_d = gpu.params_to_cls(params)
+    finally:
+        gpu.set_prestage_device(-1)
+    assert sh == sd and sh[1] != 0 and sh[0] == 0
+    for a, b in zip(th, td):
+        if a is None:
+            assert b is None
+            continue
+        # (cs2 is left out: the reference's baryon-temperature recursion of inithermo amplifies a 2e-13 change of H0 to
+        # O(1) differences in some 2600 rows of that table -- rounding noise that two runs only share bit for bit; the
+        # C_l below are what it feeds)
+        for key in ("gal_a", "gal_h", "gal_x", "tau", "vis", "dotmu", "k", "q"):
+            x, y = np.asarray(a.d[key]), np.asarray(b.d[key])
+            assert x.shape == y.shape, key
+            if x.size:
+                assert np.max(np.abs(x - y)) <= 2e-11 * np.max(np.abs(x)), key
+        for key in ("c2", "c3", "c4", "c5", "cG", "tau0"):
+            assert abs(a.d[key] - b.d[key]) <= 1e-13 * max(1.0, abs(a.d[key])), key
+    ok = ~np.isnan(cl_h[:, 0, 0])
+    assert np.array_equal(ok, ~np.isnan(cl_d[:, 0, 0]))
+    assert np.max(np.abs(cl_d[ok] / cl_h[ok] - 1)) < 1e-8
+
+
 def test_several_gpus_from_one_process(gpu):
     """The two multi-device entry points of the C ABI (parameter-batch sharding; one spectrum with its k-modes dealt over
     the devices and NCCL all-reduces of Src and iCl) on every device count the box offers, against the single-device

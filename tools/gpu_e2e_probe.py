@@ -1,5 +1,5 @@
 """Where the time of one end-to-end step (parameters -> C_l through galcamb_prestaged_to_cls_) goes: the bench's e2e
-loop with the library's host-phase timers.  usage: python tools/gpu_e2e_probe.py [batch] [steps] [host threads]"""
+loop with the library's host-phase timers.  usage: python tools/gpu_e2e_probe.py [batch] [steps] [host threads] [dev: Galileon backgrounds on the device]"""
 import os
 import sys
 import time
@@ -18,6 +18,8 @@ def main():
     threads = int(sys.argv[3]) if len(sys.argv) > 3 else (os.cpu_count() or 8)
     g = GalCamb(0)
     g.set_host_threads(threads)
+    if len(sys.argv) > 4 and sys.argv[4] == "dev":
+        g.set_prestage_device(0)
     g.set_template(np.fromfile(os.path.join(ROOT, "tests", "golden", "highL_template.f64")).reshape(7999, 4).T.copy())
 
     def to_params(P):
