@@ -316,13 +316,23 @@ def main():
     g.prestage_wait()
     barrier()
     t1 = time.perf_counter()
+    e2e_ms = {"to_cls": 0.0, "exchange": 0.0, "wait_for_prestage": 0.0}
     for i in range(args.steps):
+        ta = time.perf_counter()
         g.prestage_async(params, host_threads)
         g.prestaged_to_cls(out)
+        tb = time.perf_counter()
         exchange(out)
+        tc = time.perf_counter()
         g.prestage_wait()
+        td = time.perf_counter()
+        e2e_ms["to_cls"] += 1e3 * (tb - ta) / args.steps
+        e2e_ms["exchange"] += 1e3 * (tc - tb) / args.steps
+        e2e_ms["wait_for_prestage"] += 1e3 * (td - tc) / args.steps
     barrier()
     dt_e2e = time.perf_counter() - t1
+    e2e_ms["library_phases_last_step"] = g.host_timings()
+    e2e_ms["device_stages_last_step"] = g.timings()
     if world > 1:
         tt = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -451,6 +461,7 @@ def main():
                     "what": "parameters -> C_l in the steady state of the pipeline: every timed step runs one complete host "
                             "pre-stage (of the following batch, on the host threads behind the device work), packing, H2D, "
                             "K1-K4, D2H" + (", NCCL gather to rank 0" if world > 1 else "")},
+            "e2e_phases_ms": e2e_ms,
             "gpu_launches": int(args.steps * 6),  # evolve, spline_k, zero_delta, los, cl, cl_interp per step
             "clocks": clocks,
             "roofline": {"kernel": "evolve_batch_kernel", "bound": "fp64", "achieved": flop / t_ev / 1e12, "peak": fp64_peak,
