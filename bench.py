@@ -312,6 +312,7 @@ def main():
     # Steady state of the pipeline: the batch of the first timed step is pre-staged during the warm-up, and EVERY timed
     # step carries one complete pre-stage (of the following batch) on the host threads behind its device work.
     g.params_to_cls(params, nthreads=host_threads, out=out)  # warm-up of the whole call path
+    exchange(out)  # communicator set-up and buffer registration of the gather belong to the warm-up
     g.prestage_async(params, host_threads)
     g.prestage_wait()
     barrier()

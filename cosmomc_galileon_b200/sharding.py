@@ -19,29 +19,47 @@ def shard_models(models, rank, world):
     return models[lo:hi]
 
 
+_gather_state = {}
+
+
 def gather_cls_to_root(local_cls, n_total, device=None, root=0):
     """Gather of the per-rank C_l blocks on ONE rank (the one that feeds the likelihoods): (n_total, 3, nL) in the
     original point order on `root`, None elsewhere.  The blocks travel device to device (NCCL over NVLink when `device`
-    is a GPU); only the root copies the assembled batch back to the host."""
+    is a GPU); only the root copies the assembled batch back to the host.  The returned array is the root's (pinned,
+    reused) result buffer: valid until the next call."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(), dist.get_rank()
     nmax = max(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world))
     shape = (nmax,) + tuple(local_cls.shape[1:])
-    pad = np.zeros(shape, dtype=np.float64)
-    pad[: local_cls.shape[0]] = local_cls
-    mine = torch.from_numpy(pad)
-    if device is not None:
-        mine = mine.to(device)
-    bufs = [torch.empty(shape, dtype=torch.float64, device=mine.device) for _ in range(world)] if rank == root else None
-    dist.gather(mine, bufs, dst=root)
+    if local_cls.shape[0] == nmax and local_cls.dtype == np.float64 and local_cls.flags.c_contiguous:
+        pad = local_cls  # equal shares (the usual case): no staging copy
+    else:
+        pad = np.zeros(shape, dtype=np.float64)
+        pad[: local_cls.shape[0]] = local_cls
+    # device buffers, the root's receive blocks and its pinned result are kept across calls (one batch shape per run)
+    key = (shape, str(device), world, rank, root, n_total)
+    st = _gather_state.get(key)
+    if st is None:
+        dev = device if device is not None else torch.device("cpu")
+        st = {"mine": torch.empty(shape, dtype=torch.float64, device=dev)}
+        if rank == root:
+            st["bufs"] = [torch.empty(shape, dtype=torch.float64, device=dev) for _ in range(world)]
+            st["out"] = torch.empty((n_total,) + shape[1:], dtype=torch.float64,
+                                    pin_memory=(device is not None and torch.cuda.is_available()))
+        _gather_state.clear()
+        _gather_state[key] = st
+    st["mine"].copy_(torch.from_numpy(pad))
+    dist.gather(st["mine"], st.get("bufs"), dst=root)
     if rank != root:
         return None
-    parts = []
+    out = st["out"]
     for r in range(world):
         lo, hi = shard_range(n_total, r, world)
-        parts.append(bufs[r][: hi - lo].cpu().numpy())
-    return np.concatenate(parts, axis=0)
+        out[lo:hi].copy_(st["bufs"][r][: hi - lo], non_blocking=True)
+    if device is not None and torch.cuda.is_available():
+        torch.cuda.synchronize(device)
+    return out.numpy()
 
 
 def gather_cls(local_cls, n_total, device=None):
