@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=int(os.environ.get("GALCAMB_BENCH_BATCH", "1024")), help="parameter points per GPU per step")
+    ap.add_argument("--host-threads", type=int, default=0, help="host threads per rank (default: cores / ranks)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the N = 1 side legs (replicas, configs[2..4])")
     args = ap.parse_args()
@@ -238,7 +239,7 @@ def main():
     B = args.batch
     meta = load_meta_fixture()
     cores = os.cpu_count() or 8
-    host_threads = max(1, cores // world)
+    host_threads = args.host_threads if args.host_threads > 0 else max(1, cores // world)
     g = GalCamb(local)
     g.set_host_threads(host_threads)
     # Galileon backgrounds of a batch on the device (one lane per cosmology, next to the per-k kernel of the previous
