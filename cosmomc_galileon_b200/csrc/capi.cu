@@ -729,8 +729,10 @@ int galcamb_evolve_sources_(void) {
   CK(cudaMemcpyAsync(g.d_items, g.items.data(), nitems * sizeof(int2), cudaMemcpyHostToDevice, g.stream));
   CK(cudaMemsetAsync(g.d_counters, 0, 24 * sizeof(unsigned long long), g.stream));
   if (batch_form) {
-    const size_t nwarps = (nitems + 31) / 32;
-    const size_t ws_need = nwarps * 12 * (size_t)NV * 32;  // GC_NCOL columns (csrc/evolve_batch.cu)
+    // one slot per RESIDENT warp (persistent CTAs of up to 8 warps, csrc/evolve_batch.cu): never more than the warps of
+    // the item list rounded up to whole CTAs
+    const size_t nwarps = (nitems + 31) / 32 + 8;
+    const size_t ws_need = nwarps * 12 * (size_t)NV * 32;  // GC_NCOL columns
     if (grow(&g.d_ws, &g.ws_cap, ws_need)) return fail(100, "cudaMalloc workspace");
   }
   CK(cudaEventRecord(g.ev[0], g.stream));

@@ -1567,9 +1567,21 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
   // turned every field access into a long-scoreboard stall.  Stride = odd multiple of 8 B -> conflict-free.
   extern __shared__ unsigned char gc_smem_raw[];
   Lane& L = *reinterpret_cast<Lane*>(gc_smem_raw + (size_t)threadIdx.x * GC_LANE_STRIDE);
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  // Persistent CTAs: a CTA takes blocks of blockDim.x items off a counter, in the launcher's expensive-first order, until
+  // none is left.  Its warps keep ONE workspace slot each for the whole launch (slot = resident warp, not item), so the
+  // integrator state of everything resident is a compact range at the start of the workspace -- which the launcher
+  // can name in an L2 access-policy window.
+  __shared__ int s_block;
+  const int nblocks = (nitems + (int)blockDim.x - 1) / (int)blockDim.x;
   const int lane = threadIdx.x & 31;
-  const int gwarp = tid >> 5;
+  const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // workspace slot
+  for (;;) {
+  __syncthreads();  // every warp is done with the previous block (and has read s_block)
+  if (threadIdx.x == 0) s_block = (int)atomicAdd(&counters[16], 1ULL);
+  __syncthreads();
+  const int block = s_block;
+  if (block >= nblocks) break;
+  const int tid = block * blockDim.x + threadIdx.x;
   const bool have = tid < nitems && items[tid < nitems ? tid : 0].x >= 0;  // padding items carry model = -1
   L.phase = PH_DONE;
   L.status = 0;
@@ -1759,6 +1771,7 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
     atomicAdd(&counters[2], (unsigned long long)L.n_out);
     atomicAdd(&counters[4], (unsigned long long)L.n_shared);
   }
+  }  // next block of items
 }
 
 }  // namespace gc
@@ -1808,6 +1821,40 @@ extern "C" cudaError_t GC_ENTRY(gc_launch_evolve_batch)(const DevModel* models, 
     if (e != cudaSuccess) return e;
   }
   const int blocks = (nitems + threads - 1) / threads;
-  gc::evolve_batch_kernel<<<blocks, threads, smem, stream>>>(models, items, nitems, workspace, NV, status, counters);
-  return cudaGetLastError();
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gc::evolve_batch_kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int grid = blocks < per_sm * n_sm ? blocks : per_sm * n_sm;  // persistent: what is resident at once
+  // Experiment (off by default, it LOSES 16 %): the workspace slots of the resident warps are the first grid * warps slots;
+  // as much of that range as an access-policy window may name (128 MiB on B200) marked persisting in L2 for this launch.
+  static long l2_persist = -1;
+  if (l2_persist < 0) {
+    const char* e = getenv("GALCAMB_L2_PERSIST");  // experiment knob: 0 = no access-policy window
+    l2_persist = e ? atol(e) : 0;  // measured on 1024 distinct points: 4420 ms without the window, 5136 ms with it
+  }
+  bool window = false;
+  if (l2_persist && grid < blocks) {
+    int dev = 0, max_win = 0, max_persist = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    if (max_win > 0 && max_persist > 0) {
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+      const size_t used = (size_t)grid * (threads / 32) * GC_NCOL * NV * GC_LANES * sizeof(double);
+      cudaStreamAttrValue attr{};
+      attr.accessPolicyWindow.base_ptr = workspace;
+      attr.accessPolicyWindow.num_bytes = used < (size_t)max_win ? used : (size_t)max_win;
+      attr.accessPolicyWindow.hitRatio = 1.0f;
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+      window = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+    }
+  }
+  gc::evolve_batch_kernel<<<grid, threads, smem, stream>>>(models, items, nitems, workspace, NV, status, counters);
+  const cudaError_t rc = cudaGetLastError();
+  if (window) {  // the following kernels of the stream run without a window
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+  }
+  return rc;
 }
