@@ -122,6 +122,49 @@ __device__ __forceinline__ void hier_run(const InCol ay, double* __restrict__ ay
   }
 }
 
+// The two thermo-table rows of the lane's last look-up, kept in its shared-memory record: consecutive right-hand sides of
+// an item fall into the same interval of the 20 000-row table most of the time, and with 32 models per warp every fresh
+// look-up is 32 scattered cache lines (usually from HBM: the tables of a batch are 1.7 GB).  thermo() of evolve_device.cuh
+// with the rows taken from here when the interval is the cached one; same arithmetic.
+struct ThermoRows {
+  int i;  // 1-based lower row of the interval (0 = nothing cached)
+  double v[10];
+};
+#ifndef GC_THERMO_CACHE
+#define GC_THERMO_CACHE 1
+#endif
+__device__ __forceinline__ void thermo_cached(const DevModel& M, ThermoRows* __restrict__ tc, double tau, double& cs2b, double& opacity,
+                                              double* dopacity) {
+  const int nth = M.nthermo;
+  double d = log(tau * M.inv_tauminn) * M.inv_dlntau + 1.0;
+  if (d > nth - 0.5) d = log(tau / M.tauminn) / M.dlntau + 1.0;  // see thermo()
+  int i = (int)d;
+  d = d - i;
+  if (i >= nth) {
+    const double* r = M.th + (size_t)(nth - 1) * 5;
+    cs2b = GC_LDG(r) + (d + i - nth) * GC_LDG(r + 1);
+    opacity = GC_LDG(r + 2) + (d - nth) * GC_LDG(r + 3);
+    if (dopacity) *dopacity = 0;
+    return;
+  }
+  if (i < 1) i = 1;
+  double a[10];
+  if (tc->i == i) {
+#pragma unroll
+    for (int c = 0; c < 10; c++) a[c] = tc->v[c];
+  } else {
+    const double* r0 = M.th + (size_t)(i - 1) * 5;
+#pragma unroll
+    for (int c = 0; c < 10; c++) a[c] = GC_LDG(r0 + c);  // rows i and i + 1 are adjacent
+#pragma unroll
+    for (int c = 0; c < 10; c++) tc->v[c] = a[c];
+    tc->i = i;
+  }
+  cs2b = herm(a[0], a[1], a[5], a[6], d);
+  opacity = herm(a[2], a[3], a[7], a[8], d);
+  if (dopacity) *dopacity = herm(a[3], a[4], a[8], a[9], d) * M.inv_dlntau / tau;
+}
+
 // Nu_Integrate_L012 (camb/equations_galileon.f90:1058-1107; evolve_device.cuh) for derivs(): density and flux moments
 // only, the loads of all momentum bins issued before the sums (same terms, same order).
 __device__ __forceinline__ void nu_moments_01(const DevModel& M, const EV& e, const InCol y, double a, int nu_i, double& drhonu,
@@ -176,7 +219,7 @@ __device__ __forceinline__ void nu_moments_01(const DevModel& M, const EV& e, co
 // ---------------------------------------------------------------- derivs
 // camb/equations_galileon.f90:2098-2589.  ay / ayp are workspace columns.  Writes e.pig / e.pigdot during
 // tight coupling exactly as the reference does (its value at a switch is the one left by the LAST call).
-__device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restrict__ ep, double tau,
+__device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __restrict__ ep, ThermoRows* __restrict__ tc, double tau,
                                     const double* __restrict__ ay_, double* __restrict__ ayp) {
   const InCol ay{ay_};
   // __restrict__ on every pointer: the state-vector stores below must not force reloads of the model constants
@@ -213,7 +256,11 @@ __device__ __forceinline__ void derivs(const DevModel* __restrict__ Mp, EV* __re
     }
   }
   double cs2, opacity, dopacity = 0;
+#if GC_THERMO_CACHE
+  thermo_cached(M, tc, tau, cs2, opacity, e.TightCoupling ? &dopacity : nullptr);
+#else
   thermo(M, tau, cs2, opacity, e.TightCoupling ? &dopacity : nullptr);
+#endif
   const double cothxor = 1.0 / tau;
 #if GC_EARLY_HIER
   // The equations of the high multipoles (l >= 3 of photons, polarisation, massless neutrinos; l = 1 and l >= 3 of every
@@ -686,6 +733,8 @@ struct Lane {
 #endif
   double out_pig, out_pigdot;
   int status;
+  double tol1;    // M.tol1 (read by every pass of advance(); the model record itself is a scattered global load)
+  ThermoRows th;  // see thermo_cached()
   // work counters
   unsigned n_derivs, sum_n, n_out, n_shared;  // per lane: < 1e5 evaluations of < 200 equations
 #if GC_HOT_IN_SMEM
@@ -1231,7 +1280,7 @@ __device__ __forceinline__ void advance(Lane& L, int wphase, bool align) {
   const DevModel& M = *L.M;
   EV& e = L.e;
   const int S = M.SourceNum;
-  const double tol = M.tol1;
+  const double tol = L.tol1;
   for (;;) {
     switch (L.phase) {
       case PH_NEXT_OUTPUT: {
@@ -1612,6 +1661,8 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
     }
 #endif
     L.kidx = it.y;
+    L.tol1 = M.tol1;
+    L.th.i = 0;
     L.NV = NV;
     L.ws = workspace + (size_t)gwarp * GC_NCOL * NV * GC_LANES + lane;
     // DoSourcek, camb/cmbmain.f90:662-689
@@ -1735,9 +1786,9 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
     }
     if (need) {
 #if GC_HOT_IN_SMEM
-      derivs(reinterpret_cast<const DevModel*>(L.hot), &L.e, L.req_tau, col(L, L.req_in), col(L, L.req_out));
+      derivs(reinterpret_cast<const DevModel*>(L.hot), &L.e, &L.th, L.req_tau, col(L, L.req_in), col(L, L.req_out));
 #else
-      derivs(L.M, &L.e, L.req_tau, col(L, L.req_in), col(L, L.req_out));
+      derivs(L.M, &L.e, &L.th, L.req_tau, col(L, L.req_in), col(L, L.req_out));
 #endif
       L.want_derivs = false;
       L.n_derivs++;
