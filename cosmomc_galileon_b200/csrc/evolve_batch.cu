@@ -130,6 +130,9 @@ struct ThermoRows {
   int i;  // 1-based lower row of the interval (0 = nothing cached)
   double v[10];
 };
+#ifndef GC_LOCKSTEP_EVERY
+#define GC_LOCKSTEP_EVERY 1
+#endif
 #ifndef GC_THERMO_CACHE
 #define GC_THERMO_CACHE 1
 #endif
@@ -1780,7 +1783,10 @@ __global__ void __launch_bounds__(GC_EVOLVE_THREADS, GC_EVOLVE_MINBLOCKS) evolve
     const bool need = L.want_derivs;
     const bool alive = L.phase != PH_DONE || need;
     if (blockDim.x > 32) {
-      if (!__syncthreads_or(alive)) break;
+      // lock step: every GC_LOCKSTEP_EVERY-th round (a power of two) the warps of the CTA meet here
+      if ((wphase & (GC_LOCKSTEP_EVERY - 1)) == 0) {
+        if (!__syncthreads_or(alive)) break;
+      }
     } else {
       if (!__any_sync(0xffffffffu, alive)) break;
     }
