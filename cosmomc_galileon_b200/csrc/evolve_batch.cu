@@ -130,6 +130,10 @@ struct ThermoRows {
   int i;  // 1-based lower row of the interval (0 = nothing cached)
   double v[10];
 };
+// row 5 of the tableau formed by the pass of row 4 (same columns): seven stage-combination passes per step instead of eight
+#ifndef GC_FUSE_ROW5
+#define GC_FUSE_ROW5 (GC_K8_IN_K2)
+#endif
 #ifndef GC_LOCKSTEP_EVERY
 #define GC_LOCKSTEP_EVERY 1
 #endif
@@ -819,11 +823,12 @@ __constant__ unsigned c_rowmask[8] = {0x01, 0x03, 0x07, 0x0f, 0x1f, 0x1f, 0x5f, 
 #define GC_LDY(p) (*(p))
 #endif
 
-template <int NC, int U, bool ROW0, bool FIN>
+template <int NC, int U, bool ROW0, bool FIN, bool DUAL>
 __device__ __forceinline__ int combine_uniform(int i, int nend, const double* __restrict__ y, double* __restrict__ w9,
                                                const double* const* kc, const double* cf, const double* ce, double temp,
                                                bool stash, bool stash_k1, double* __restrict__ ys,
-                                               double* __restrict__ ks, double& errn, double& ynew) {
+                                               double* __restrict__ ks, double& errn, double& ynew, double* __restrict__ w8,
+                                               const double* cf2) {
   auto load = [&](int i0, double (&yv)[U], double (&kv)[NC][U]) {
 #pragma unroll
     for (int u = 0; u < U; u++) yv[u] = GC_LDY(&AT(y, i0 + u));
@@ -845,6 +850,12 @@ __device__ __forceinline__ int combine_uniform(int i, int nend, const double* __
         v = yv[u] + temp * acc;
       }
       AT(w9, i0 + u) = v;
+      if (DUAL) {  // the row after this one reads the same columns: its stage input from the same loads (see GC_FUSE_ROW5)
+        double acc2 = kv[0][u] * cf2[0];
+#pragma unroll
+        for (int c = 1; c < NC; c++) acc2 = acc2 + kv[c][u] * cf2[c];
+        AT(w8, i0 + u) = yv[u] + temp * acc2;
+      }
       if (ROW0) {
         if (stash) AT(ys, i0 + u) = yv[u];
         if (stash_k1) AT(ks, i0 + u) = kv[0][u];
@@ -906,19 +917,22 @@ __host__ __device__ constexpr int combine_batch(int NC) {
 template <int R>
 __device__ __forceinline__ int combine_uniform_row(int i, int nend, const double* __restrict__ y, double* __restrict__ w9,
                                                    const double* const* kc, double temp, bool stash, bool stash_k1,
-                                                   double* __restrict__ ys, double* __restrict__ ks, double& errn, double& ynew) {
+                                                   double* __restrict__ ys, double* __restrict__ ks, double& errn, double& ynew,
+                                                   double* __restrict__ w8) {
   constexpr int NC = R == 0 ? 1 : R == 1 ? 2 : R == 2 ? 3 : R == 3 ? 4 : R <= 5 ? 5 : R == 6 ? 6 : 7;
   constexpr int U = combine_batch(NC);
   const double* kk[NC];
-  double cfk[NC], cek[NC];
+  double cfk[NC], cek[NC], cf2k[NC];
 #pragma unroll
   for (int j = 0; j < NC; j++) {
     const int c = R == 6 ? (j < 5 ? j : 6) : R == 7 ? (j == 0 ? 0 : j + 1) : j;
     kk[j] = kc[c];
     cfk[j] = c_row[R][c];
     cek[j] = R == 7 ? c_err[c] : 0.0;
+    cf2k[j] = R == 4 ? c_row[5][c] : 0.0;
   }
-  return combine_uniform<NC, U, R == 0, R == 7>(i, nend, y, w9, kk, cfk, cek, temp, stash, stash_k1, ys, ks, errn, ynew);
+  return combine_uniform<NC, U, R == 0, R == 7, (GC_FUSE_ROW5 && R == 4)>(i, nend, y, w9, kk, cfk, cek, temp, stash, stash_k1, ys, ks,
+                                                                          errn, ynew, w8, cf2k);
 }
 
 // ONE stage-combination routine for every row of the tableau, executed by the whole warp together: each lane brings
@@ -951,6 +965,11 @@ __device__ __forceinline__ void combine(Lane& L) {
 #endif
   const double temp = L.htrial / 1398169080000.0;
   double errn = 0.0, ynew = 0.0;
+  // GC_FUSE_ROW5: row 5 of the tableau (the input of stage 7) reads k1..k5 like row 4 and does not need k6, so the pass of
+  // row 4 forms it as well, into column 8 (free: k8 lives in k2's column), and the state machine skips the pass of row 5
+  const bool dual = GC_FUSE_ROW5 && on && r == 4;
+  const bool any_dual = GC_FUSE_ROW5 && __any_sync(0xffffffffu, dual);
+  double* __restrict__ w8 = ws_of(L) + (size_t)8 * L.NV * GC_LANES;
   // a lane whose last output is still pending keeps a copy of that y (this is the first pass over y since then)
   const bool stash = on && L.out_pending && !L.out_stashed;
   double* __restrict__ ys = ws_of(L) + (size_t)10 * L.NV * GC_LANES;
@@ -964,14 +983,14 @@ __device__ __forceinline__ void combine(Lane& L) {
   if (same_row && nmin >= 4 && nmin != 0x7fffffff) {
     if (on) {  // padding lanes of a short k group sit this out
       switch (r) {  // warp-uniform here
-        case 0: i = combine_uniform_row<0>(i, nmin, y, w9, kc, temp, stash, stash_k1, ys, ks, errn, ynew); break;
-        case 1: i = combine_uniform_row<1>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew); break;
-        case 2: i = combine_uniform_row<2>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew); break;
-        case 3: i = combine_uniform_row<3>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew); break;
-        case 4: i = combine_uniform_row<4>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew); break;
-        case 5: i = combine_uniform_row<5>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew); break;
-        case 6: i = combine_uniform_row<6>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew); break;
-        default: i = combine_uniform_row<7>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew); break;
+        case 0: i = combine_uniform_row<0>(i, nmin, y, w9, kc, temp, stash, stash_k1, ys, ks, errn, ynew, w8); break;
+        case 1: i = combine_uniform_row<1>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew, w8); break;
+        case 2: i = combine_uniform_row<2>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew, w8); break;
+        case 3: i = combine_uniform_row<3>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew, w8); break;
+        case 4: i = combine_uniform_row<4>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew, w8); break;
+        case 5: i = combine_uniform_row<5>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew, w8); break;
+        case 6: i = combine_uniform_row<6>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew, w8); break;
+        default: i = combine_uniform_row<7>(i, nmin, y, w9, kc, temp, false, false, ys, ks, errn, ynew, w8); break;
       }
     }
     {  // first element the uniform loops did not cover (same for every lane)
@@ -1014,6 +1033,16 @@ __device__ __forceinline__ void combine(Lane& L) {
       for (int c = 0; c < 8; c++)
 #pragma unroll
         for (int u = 0; u < 4; u++) a2[u] = a2[u] + kv[c][u] * ce[c];
+    }
+    if (any_dual) {  // lanes in row 4 form row 5 as well (its columns are 0..4)
+      double a3[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int c = 0; c < 5; c++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) a3[u] = a3[u] + kv[c][u] * (dual ? c_row[5][c] : 0.0);
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (dual && p[u]) AT(w8, i + u) = yv[u] + temp * a3[u];
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
@@ -1065,6 +1094,7 @@ __device__ __forceinline__ void combine_group(unsigned char* smem_base, int nown
   const bool stash_k1 = stash && O.stash_k1;
   double* __restrict__ ys = ws_of(O) + (size_t)10 * O.NV * GC_LANES;
   double* __restrict__ ks = ws_of(O) + (size_t)11 * O.NV * GC_LANES;
+  double* __restrict__ w8 = ws_of(O) + (size_t)8 * O.NV * GC_LANES;
   const int nmax = __reduce_max_sync(0xffffffffu, n);
   double errn = 0.0, ynew = 0.0;
   for (int i0 = 1 + sub; i0 <= nmax; i0 += 4 * gsz) {
@@ -1091,6 +1121,12 @@ __device__ __forceinline__ void combine_group(unsigned char* smem_base, int nown
         for (int c = 0; c < 8; c++) a1 = a1 + kv[c][u] * c_row[r][c];
         const double v = (r == 0) ? yv[u] + temp * kv[0][u] * 233028180000.0 : yv[u] + temp * a1;
         AT(w9, i) = v;
+        if (GC_FUSE_ROW5 && r == 4) {  // row 5 from the same loads (see combine())
+          double a3 = 0.0;
+#pragma unroll
+          for (int c = 0; c < 5; c++) a3 = a3 + kv[c][u] * c_row[5][c];
+          AT(w8, i) = yv[u] + temp * a3;
+        }
         if (stash) AT(ys, i) = yv[u];
         if (stash_k1) AT(ks, i) = kv[0][u];
         if (fin) {
@@ -1477,8 +1513,9 @@ __device__ __forceinline__ void advance(Lane& L, int wphase, bool align) {
         const int s = L.stage;  // the stage whose derivative has just been written (2..8)
         const double x = L.tau;
         if (s < 8) {
-          // input of stage s+1 : row s-1 of the tableau, formed by the warp-wide combine()
-          L.crow = s - 1;
+          // input of stage s+1 : row s-1 of the tableau, formed by the warp-wide combine() -- except the input of stage 7
+          // (row 5), which the pass of row 4 has already left in column 8 (GC_FUSE_ROW5)
+          L.crow = (GC_FUSE_ROW5 && s == 6) ? -1 : s - 1;
           double frac;
           switch (s) {
             case 2: frac = 4.0 / 15.0; break;
@@ -1494,7 +1531,7 @@ __device__ __forceinline__ void advance(Lane& L, int wphase, bool align) {
             L.req_tau = x + L.htrial / 15.0;
           else
             L.req_tau = x + L.htrial * frac;
-          L.req_in = 9;
+          L.req_in = (GC_FUSE_ROW5 && s == 6) ? 8 : 9;
           L.req_out = (GC_K8_IN_K2 && s == 7) ? 2 : s + 1;
           L.want_derivs = true;
           L.stage = s + 1;
