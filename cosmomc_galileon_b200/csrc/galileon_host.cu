@@ -708,6 +708,8 @@ int gc_galileon_background_device(int device, const GcBackgroundIn* in, int n, c
   do {                                   \
     if ((call) != cudaSuccess) return 100; \
   } while (0)
+  for (int i = 0; i < n; i++)
+    if (in[i].neig > 0 && (nu_tab == nullptr || nu_rows == 0)) return 100;  // no neutrino tables: the caller integrates on the host
   GCB(cudaSetDevice(device));
   const std::vector<double>& nodes = background_nodes();
   if (DB.device != device) {
